@@ -1,0 +1,97 @@
+"""ctypes loader for the C restatement (oracle/sr_oracle.c).  TEST INFRASTRUCTURE ONLY."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+RINGS = {"goldilocks": 0, "babybear": 1, "stark_prime": 2, "gl": 0, "bb": 1, "sp": 2}
+_lib = None
+
+
+def _bind(path):
+    L = ctypes.CDLL(path)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    L.sro_elem_words.restype = ctypes.c_size_t
+    L.sro_elem_words.argtypes = [ctypes.c_int]
+    for name in ("sro_crt", "sro_icrt"):
+        getattr(L, name).argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_int]
+        getattr(L, name).restype = None
+    L.sro_ntt_mul.argtypes = [ctypes.c_int, u64p, u64p, ctypes.c_size_t, ctypes.c_int]
+    L.sro_ntt_mul.restype = None
+    L.sro_ring_mul.argtypes = [ctypes.c_int, u64p, u64p, u64p, ctypes.c_size_t, ctypes.c_int]
+    L.sro_ring_mul.restype = None
+    L.sro_matvec.argtypes = [ctypes.c_int, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p,
+                             ctypes.c_size_t, u64p, ctypes.c_int]
+    L.sro_matvec.restype = ctypes.c_int
+    L.sro_crt_stages.argtypes = [ctypes.c_int, u64p]
+    L.sro_crt_stages.restype = None
+    return L
+
+
+def lib():
+    """Load oracle/libsr_oracle.so (portable x86-64-v3 build), building it if missing."""
+    global _lib
+    if _lib is None:
+        path = os.path.join(HERE, "libsr_oracle.so")
+        if not os.path.exists(path):
+            subprocess.run(["make", "-s", "-C", HERE, "libsr_oracle.so"], check=True)
+        _lib = _bind(path)
+    return _lib
+
+
+def lib_native():
+    """Rebuild with -march=native on THIS machine (the timed CPU baseline on the GPU box's own
+    host cores); falls back to the portable build if no compiler is available."""
+    npath = os.path.join(HERE, "libsr_oracle_native.so")
+    try:
+        subprocess.run(["gcc", "-O3", "-march=native", "-fPIC", "-std=gnu11", "-shared", "-o", npath,
+                        os.path.join(HERE, "sr_oracle.c"), "-lpthread"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return _bind(npath), "native"
+    except Exception:
+        return lib(), "x86-64-v3"
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+
+def words(ring):
+    return {0: 24, 1: 72, 2: 64}[RINGS[ring]]
+
+
+def crt(ring, buf, threads=1, L=None):
+    """In place on a uint64 array of n*words limbs; returns it."""
+    (L or lib()).sro_crt(RINGS[ring], _p(buf), buf.size // words(ring), threads)
+    return buf
+
+
+def icrt(ring, buf, threads=1, L=None):
+    (L or lib()).sro_icrt(RINGS[ring], _p(buf), buf.size // words(ring), threads)
+    return buf
+
+
+def ntt_mul(ring, a, b, threads=1, L=None):
+    (L or lib()).sro_ntt_mul(RINGS[ring], _p(a), _p(b), a.size // words(ring), threads)
+    return a
+
+
+def ring_mul(ring, a, b, threads=1, L=None):
+    out = np.empty_like(a)
+    (L or lib()).sro_ring_mul(RINGS[ring], _p(a), _p(b), _p(out), a.size // words(ring), threads)
+    return out
+
+
+def matvec(ring, rows, v, threads=1, L=None):
+    """rows: list of uint64 arrays (m*words each); v: uint64 array.  Returns kappa*words array or None."""
+    w = words(ring)
+    kappa = len(rows)
+    m = rows[0].size // w if kappa else 0
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    arr = (u64p * max(kappa, 1))(*[_p(r) for r in rows])
+    out = np.zeros(kappa * w, dtype=np.uint64)
+    rc = (L or lib()).sro_matvec(RINGS[ring], arr, kappa, m, _p(v), v.size // w, _p(out), threads)
+    return None if rc else out

@@ -1,0 +1,80 @@
+"""oracle/sr_oracle.c (C restatement, raw Montgomery limbs) == oracle/ref_py.py (big ints)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as C
+from oracle import ref_py as O
+
+ALL = ["goldilocks", "babybear", "stark_prime"]
+
+
+def raw(M, vals):
+    return np.array(O.to_raw(M, vals), dtype=np.uint64)
+
+
+def rand_elems(M, n, rng):
+    return [[rng.randrange(M.p) for _ in range(M.D)] for _ in range(n)]
+
+
+def flat(M, elems):
+    return np.concatenate([raw(M, e) for e in elems])
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_golden_derived_vectors(name, golden):
+    g, M = golden(name + "_derived"), O.MODELS[name]
+    for case in g["cases"]:
+        a = np.array([int(x) for x in case["a_raw"]], dtype=np.uint64)
+        b = raw(M, [int(x) for x in case["b"]])
+        want_crt = np.array([int(x) for x in case["crt_a_raw"]], dtype=np.uint64)
+        want_mul = np.array([int(x) for x in case["ring_mul_raw"]], dtype=np.uint64)
+        assert np.array_equal(C.crt(name, a.copy()), want_crt)
+        assert np.array_equal(C.icrt(name, want_crt.copy()), a)
+        assert np.array_equal(C.ring_mul(name, a, b), want_mul)
+        nm = C.ntt_mul(name, want_crt.copy(), C.crt(name, b.copy()))
+        assert np.array_equal(nm, raw(M, [int(x) for x in case["ntt_mul"]]))
+    mv = g["matvec"]
+    rows = [np.concatenate([np.array([int(x) for x in e], dtype=np.uint64) for e in row]) for row in mv["rows_raw"]]
+    v = np.concatenate([np.array([int(x) for x in e], dtype=np.uint64) for e in mv["v_raw"]])
+    y = np.concatenate([np.array([int(x) for x in e], dtype=np.uint64) for e in mv["y_raw"]])
+    assert np.array_equal(C.matvec(name, rows, v), y)
+    assert C.matvec(name, rows, v[: v.size - C.words(name)]) is None
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_reference_kats_through_c(name, golden):
+    g, M = golden(name), O.MODELS[name]
+    for kat in g["crt_kats"]:
+        coeffs = [int(x) for x in kat["coeffs"]]
+        got = C.crt(name, raw(M, coeffs))
+        want = M.crt(coeffs)
+        assert O.from_raw(M, got.tolist()) == want
+        key = "evaluations" if name == "stark_prime" else "slot_remainders"
+        assert M.dehomogenize(want) == [int(x) for x in kat[key]]
+        assert O.from_raw(M, C.icrt(name, got.copy()).tolist()) == coeffs
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_random_batches_and_threads(name):
+    M = O.MODELS[name]
+    rng = random.Random(11)
+    n = 37
+    A, B = rand_elems(M, n, rng), rand_elems(M, n, rng)
+    # edge values
+    A[0] = [0] * M.D
+    A[1] = [M.p - 1] * M.D
+    B[1] = [M.p - 1] * M.D
+    A[2] = [1] + [0] * (M.D - 1)
+    a, b = flat(M, A), flat(M, B)
+    want_crt = flat(M, [M.crt(x) for x in A])
+    got1 = C.crt(name, a.copy(), threads=1)
+    got4 = C.crt(name, a.copy(), threads=4)
+    assert np.array_equal(got1, want_crt) and np.array_equal(got4, want_crt)
+    assert np.array_equal(C.icrt(name, got4.copy(), threads=3), a)
+    want_mul = flat(M, [O.ring_mul(M, x, y) for x, y in zip(A[:8], B[:8])])
+    w = C.words(name)
+    assert np.array_equal(C.ring_mul(name, a[: 8 * w].copy(), b[: 8 * w].copy(), threads=2), want_mul)
+    # empty batch
+    assert C.crt(name, np.zeros(0, dtype=np.uint64)).size == 0
