@@ -1,0 +1,357 @@
+#!/usr/bin/env python3
+"""Benchmark of the stark-rings hot path on B200 (contract: see the task statement / DESIGN.md).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload ringmul|commit] [--ring bb|gl|sp] [--log2n L]
+
+Default workload = BASELINE.json configs[1]: BabyBear ring, batched CRT -> slot mul -> ICRT on 2^24
+elements per GPU (weak scaling: every rank owns its own 2^24-element shard, no data-path
+collective).  A "step" is one pass of the fused ring-mul kernel over the rank's resident batch
+(inputs 2 x 9.66 GB >> 126 MB L2, so no L2 flush is needed between steps).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RING_NAMES = {"bb": "babybear", "gl": "goldilocks", "sp": "stark_prime"}
+ELEM_BYTES = {"bb": 576, "gl": 192, "sp": 512}
+P = {"bb": 2013265921, "gl": 18446744069414584321}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def gen_raw_device(torch, tag, n, seed, device):
+    """n elements of uniformly random canonical residues as raw limbs, generated on the device."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    if tag == "bb":
+        return torch.randint(0, P["bb"], (n * 72,), dtype=torch.int64, device=device, generator=g)
+    if tag == "gl":
+        # uniform 64-bit patterns, folded below p (p = 2^64 - 2^32 + 1: subtract p from the top 2^32-1 values)
+        x = torch.randint(-(1 << 63), (1 << 63) - 1, (n * 24,), dtype=torch.int64, device=device, generator=g)
+        # as unsigned, x >= p  <=>  high word == 0xFFFFFFFF and low word != 0
+        hi_all = (x >> 32) == -1
+        lo_nz = (x & 0xFFFFFFFF) != 0
+        return torch.where(hi_all & lo_nz, x + 0xFFFFFFFF, x)  # x - p  ==  x + 2^32 - 1 (mod 2^64)
+    x = torch.randint(-(1 << 63), (1 << 63) - 1, (n * 64,), dtype=torch.int64, device=device, generator=g)
+    x[3::4] &= (1 << 59) - 1  # every field element < 2^251 < p
+    return x
+
+
+def cpu_reference_rate(tag, sample_elems, threads, repeats=1):
+    """ring muls/s of the C restatement (oracle/sr_oracle.c, -march=native) on this host."""
+    import numpy as np
+    from oracle import c_oracle as C
+    from tests.util import rand_raw
+    name = RING_NAMES[tag]
+    lib, kind = C.lib_native()
+    a, b = rand_raw(name, sample_elems, 11, edge=False), rand_raw(name, sample_elems, 12, edge=False)
+    C.ring_mul(name, a[: 1024 * C.words(name)], b[: 1024 * C.words(name)], threads=1, L=lib)  # warm
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        C.ring_mul(name, a, b, threads=threads, L=lib)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or dt < best else best
+    return sample_elems / best, best, kind
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm (C restatement: the Rust crate cannot be
+    built here) on the box's host cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tag = args.ring
+    cores = os.cpu_count() or 1
+    sample = min(1 << args.log2n, args.cpu_sample)
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, dt, kind = cpu_reference_rate(tag, sample, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "ring muls/sec (CRT->mul->ICRT)", "value": value, "unit": "ring_mul/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if tag != "bb" else "u32",
+        "data": "synthetic",
+        "config": {"workload": "%s ring: batched CRT->slot mul->ICRT on 2^%d elements" % (RING_NAMES[tag], args.log2n),
+                   "ring": RING_NAMES[tag], "log2_elements_per_gpu": args.log2n,
+                   "note": "CPU arm: each step is a bounded sample of %d elements of that workload" % sample},
+        "cpu_baseline": {"value": value, "unit": "ring_mul/s", "cores": cores, "kind": "port",
+                         "sample": "%d elements per step, %s build of oracle/sr_oracle.c (C restatement of the "
+                                   "reference algorithm; the Rust crate cannot be built in this image)" % (sample, kind)},
+        "e2e": {"value": value, "unit": "ring_mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ringmul", choices=["ringmul", "commit"])
+    ap.add_argument("--ring", default=None, choices=["bb", "gl", "sp"])
+    ap.add_argument("--log2n", type=int, default=None, help="log2 elements per GPU (ringmul) / columns (commit)")
+    ap.add_argument("--kappa", type=int, default=4)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="elements in the CPU baseline sample")
+    ap.add_argument("--e2e-log2n", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.ring is None:
+        args.ring = "gl" if args.workload == "commit" else "bb"
+    if args.log2n is None:
+        args.log2n = 20 if args.workload == "commit" else {"bb": 24, "gl": 24, "sp": 20}[args.ring]
+    if args.warmup < 3:
+        args.warmup = 3 if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import stark_rings_b200 as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = S.Context(local)
+    ctx.use_torch_stream()
+    tag = args.ring
+    cfg = S.CONFIGS[tag]
+    hbm_peak, peak_src = peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = 1 << args.log2n
+    line = {}
+    if args.workload == "ringmul":
+        a = gen_raw_device(torch, tag, n, 0x5EED ^ (1000 * rank + 1), dev)
+        b = gen_raw_device(torch, tag, n, 0x5EED ^ (1000 * rank + 2), dev)
+        out = torch.empty_like(a)
+        step = lambda: cfg.ring_mul_batch(a, b, out=out, ctx=ctx)
+        units_per_step = n
+        alg_bytes_per_unit = 3 * ELEM_BYTES[tag]
+        metric, unit = "ring muls/sec (CRT->mul->ICRT)", "ring_mul/s"
+        workload = "%s ring: batched CRT->slot mul->ICRT on 2^%d elements per GPU" % (RING_NAMES[tag], args.log2n)
+    else:
+        # Goldilocks Ajtai-style commit: kappa x m matrix times vector, columns sharded over ranks
+        m_local = n // world
+        rows = [S.RqNTT(cfg, gen_raw_device(torch, tag, m_local, 0x5EED ^ (1000 * rank + 10 + i), dev), ctx)
+                for i in range(args.kappa)]
+        v = S.RqNTT(cfg, gen_raw_device(torch, tag, m_local, 0x5EED ^ (1000 * rank + 3), dev), ctx)
+        A = S.Matrix(rows, ctx)
+        limbs = cfg.limbs
+        gathered = torch.empty(world * args.kappa * limbs, dtype=torch.int64, device=dev)
+        result = torch.empty(args.kappa * limbs, dtype=torch.int64, device=dev)
+        import ctypes
+        from stark_rings_b200 import _lib as L
+
+        def step():
+            part = A.partial_mul_vec(v)
+            if dist is not None:
+                dist.all_gather_into_tensor(gathered, part.data)  # raw limbs; an NCCL sum cannot reduce mod p
+                if rank == 0:
+                    ctx.check(L.lib.sr_modsum_partials(ctx.h, cfg.ring_id, ctypes.c_void_p(gathered.data_ptr()),
+                                                       world, args.kappa, ctypes.c_void_p(result.data_ptr()),
+                                                       L.SR_DEVICE), "modsum")
+            return part
+        units_per_step = 1
+        alg_bytes_per_unit = (args.kappa * m_local + m_local + args.kappa) * ELEM_BYTES[tag]
+        metric, unit = "commits/sec (kappa x m ring matrix x vector)", "commit/s"
+        workload = "%s commit: %d x 2^%d ring matrix x vector, columns sharded over %d GPU(s)" % (
+            RING_NAMES[tag], args.kappa, args.log2n, world)
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ctx.kernel_launches - launches0
+    ms_per_step = total_ms / args.steps
+    strong = args.workload == "commit"
+    value = (units_per_step * (1 if strong else world)) / (ms_per_step / 1e3)
+
+    # roofline of the dominant kernel: its own launches, timed alone with events on the same stream
+    ktimes = []
+    for _ in range(min(args.steps, 5)):
+        ctx.timer_start()
+        step()
+        ktimes.append(ctx.timer_stop())
+    k_ms = sum(ktimes) / len(ktimes)
+    if args.workload == "ringmul":
+        achieved = alg_bytes_per_unit * units_per_step / (k_ms / 1e3) / 1e9
+    else:
+        achieved = alg_bytes_per_unit / (k_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": alg_bytes_per_unit * (units_per_step if args.workload == "ringmul" else 1)}
+
+    # ---- end to end through the C ABI with HOST buffers -----------------------------------------
+    e2e = None
+    if not args.no_e2e and args.workload == "ringmul":
+        e2e_n = 1 << (args.e2e_log2n if args.e2e_log2n is not None else args.log2n)
+        e2e = None
+        while e2e is None and e2e_n >= 1 << 10:
+            try:
+                words = e2e_n * cfg.limbs
+                ha = torch.empty(words, dtype=torch.int64).pin_memory()
+                hb = torch.empty(words, dtype=torch.int64).pin_memory()
+                ho = torch.empty(words, dtype=torch.int64).pin_memory()
+                ha.copy_(a[:words])
+                hb.copy_(b[:words])
+                torch.cuda.synchronize()
+                cfg.ring_mul_batch(ha, hb, out=ho, ctx=ctx)  # warm-up (allocates the staging ring)
+                k = max(1, min(args.steps, 3))
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(k):
+                    cfg.ring_mul_batch(ha, hb, out=ho, ctx=ctx)  # synchronous: returns when `ho` is complete
+                torch.cuda.synchronize()
+                dt = max_over_ranks((time.perf_counter() - t0) / k)
+                if rank == 0:
+                    assert torch.equal(ho[: 64 * cfg.limbs].to(dev), out[: 64 * cfg.limbs])
+                e2e = {"value": e2e_n * world / dt, "unit": unit, "h2d_bytes_per_step": 2 * words * 8,
+                       "d2h_bytes_per_step": words * 8, "elements_per_gpu": e2e_n, "ms_per_step": dt * 1e3,
+                       "note": "sr_ring_mul_batch(SR_HOST) on pinned host buffers: chunked H2D -> kernel -> D2H pipeline"}
+                del ha, hb, ho
+            except RuntimeError as ex:  # pinned allocation failed: halve
+                e2e = None
+                e2e_n //= 2
+                last = str(ex)[:120]
+        if e2e is None:
+            e2e = {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "note": "pinned host allocation failed: " + last}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu and world == 1 and args.workload == "ringmul":
+        cores = os.cpu_count() or 1
+        sample = min(n, args.cpu_sample)
+        rate, dt, kind = cpu_reference_rate(tag, sample, cores)
+        rate1, dt1, _ = cpu_reference_rate(tag, max(1024, sample // 16), 1)
+        cpu = {"value": rate, "unit": unit, "cores": cores, "kind": "port",
+               "sample": "%d elements (%.1f s wall on %d threads), %s build of oracle/sr_oracle.c" % (sample, dt, cores, kind),
+               "value_1thread": rate1}
+
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "u32" if tag == "bb" else "u64", "data": "synthetic",
+            "config": {"workload": workload, "ring": RING_NAMES[tag], "log2_elements_per_gpu": args.log2n,
+                       "l2": "inputs >> L2 (no flush needed)" if n * ELEM_BYTES[tag] > (256 << 20) else "inputs fit L2",
+                       "layout": "reference layout: u64 Montgomery limbs, %d B per element" % ELEM_BYTES[tag]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        if args.workload == "commit":
+            line["config"]["kappa"] = args.kappa
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

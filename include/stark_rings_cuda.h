@@ -1,0 +1,130 @@
+/* stark_rings_cuda.h -- C ABI of libstarkrings_cuda.so (sm_100a).
+ *
+ * Drop-in boundary for the hot path of NethermindEth/stark-rings: the bodies of the Rust items
+ * cited below become calls into these entry points (INTEGRATION.md shows the build.rs / extern "C"
+ * shim).  All buffers are the reference's own memory layout: dense arrays of ring elements, each
+ * element D field elements, each field element N little-endian u64 limbs holding x * 2^(64 N) mod p
+ * (ark-ff MontBackend), canonical (< p).
+ *
+ *   ring            p                          D   N   limbs/element   bytes/element
+ *   SR_GOLDILOCKS   2^64 - 2^32 + 1            24  1   24              192
+ *   SR_BABYBEAR     15 * 2^27 + 1              72  1   72              576
+ *   SR_STARK        2^251 + 17 * 2^192 + 1     16  4   64              512
+ *
+ * Lengths are given in u64 LIMBS of the flat slice (what `Flatten::flatten_to_coeffs`,
+ * flatten.rs:10-18, exposes), so a wrong slice length is detectable: a length that is not a
+ * multiple of limbs/element returns SR_ERR_BAD_LENGTH where the reference panics
+ * (assert_eq!(coefficients.len(), D): goldilocks/ntt.rs:136,241, babybear/ntt.rs:144,239,
+ * stark_prime/ntt.rs:122,246).
+ *
+ * `loc` says where the caller's buffers live: SR_HOST (any host memory; pinned memory from
+ * sr_host_alloc moves fastest) or SR_DEVICE (device memory of the context's GPU, e.g. from
+ * sr_dev_alloc; must be 16-byte aligned).  Host calls are synchronous; device calls are enqueued
+ * on the context's stream (sr_sync / sr_set_stream).
+ *
+ * There is no CPU fallback: without a usable CUDA device sr_init fails with SR_ERR_CUDA.
+ * Thread safety: a context serialises its own calls with an internal mutex; use one context per
+ * host thread for concurrency.  The library never frees or retains caller pointers past return.
+ */
+#ifndef STARK_RINGS_CUDA_H
+#define STARK_RINGS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sr_ctx sr_ctx;
+
+enum sr_status {
+    SR_OK = 0,
+    SR_ERR_BAD_LENGTH = 1,  /* slice length not a multiple of limbs/element, or ncols != v.len() */
+    SR_ERR_CUDA = 2,        /* CUDA runtime error; text in sr_last_error */
+    SR_ERR_INVALID = 3,     /* null/misaligned pointer, unknown ring/loc */
+    SR_ERR_NOMEM = 4
+};
+enum sr_ring { SR_GOLDILOCKS = 0, SR_BABYBEAR = 1, SR_STARK = 2 };
+enum sr_loc { SR_HOST = 0, SR_DEVICE = 1 };
+
+/* ---- context ---------------------------------------------------------------------------- */
+int sr_init(int device, sr_ctx** out);
+int sr_destroy(sr_ctx* ctx);
+const char* sr_last_error(sr_ctx* ctx);       /* message of the last failing call on ctx */
+const char* sr_version(void);
+int sr_set_stream(sr_ctx* ctx, void* cuda_stream); /* use a caller-owned cudaStream_t for device calls */
+int sr_sync(sr_ctx* ctx);
+size_t sr_elem_limbs(int ring);               /* 24 / 72 / 64; 0 for an unknown ring */
+uint64_t sr_kernel_launches(sr_ctx* ctx);     /* kernels launched by this context so far */
+
+/* ---- memory ------------------------------------------------------------------------------ */
+int sr_dev_alloc(sr_ctx* ctx, size_t bytes, void** dptr);
+int sr_dev_free(sr_ctx* ctx, void* dptr);
+int sr_host_alloc(sr_ctx* ctx, size_t bytes, void** hptr); /* pinned host memory */
+int sr_host_free(sr_ctx* ctx, void* hptr);
+int sr_h2d(sr_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);  /* async on ctx stream */
+int sr_d2h(sr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* async on ctx stream */
+
+/* ---- timing on the context's stream (CUDA events) ---------------------------------------- */
+int sr_timer_start(sr_ctx* ctx);
+int sr_timer_stop(sr_ctx* ctx, float* ms);    /* synchronises; elapsed since sr_timer_start */
+
+/* ---- batched conversions and products ------------------------------------------------------
+ * Replaces  CRT::elementwise_crt / ICRT::elementwise_icrt            (crt.rs:10-25, 34-49)
+ *           CyclotomicConfig::{crt_in_place, icrt_in_place}           (ring_config.rs:27,34)
+ *           impl_crt_icrt_for_a_ring!: crt(self) / icrt(self)         (crt.rs:52-77), n = 1 element
+ * In place: `buf` holds n_limbs limbs of coefficient-form (crt) / NTT-form (icrt) elements and is
+ * overwritten with the other form, exactly as the reference retypes the same allocation. */
+int sr_crt_batch(sr_ctx* ctx, int ring, uint64_t* buf, size_t n_limbs, int loc);
+int sr_icrt_batch(sr_ctx* ctx, int ring, uint64_t* buf, size_t n_limbs, int loc);
+
+/* Replaces  Mul / MulAssign / MulUnchecked for CyclotomicPolyRingNTTGeneral
+ *           (ntt_form.rs:159-189, 213-225, 521-550): a[i] <- a[i] * b[i] slot-wise, NTT form. */
+int sr_ntt_mul_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, const uint64_t* b, size_t n_limbs, int loc);
+
+/* Replaces  Mul for CyclotomicPolyRingGeneral (coeff_form.rs:54-67, 250-258): out[i] = a[i] * b[i]
+ * in F_p[X]/Phi, coefficient form in and out; computed as icrt(crt(a) * crt(b)) in one kernel
+ * (the identity the reference pins in test_mul_crt, e.g. goldilocks/mod.rs:231-247).
+ * out may alias a or b. */
+int sr_ring_mul_batch(sr_ctx* ctx, int ring, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                      size_t n_limbs, int loc);
+
+/* ---- ring matrix x vector (Ajtai-style commitment) -------------------------------------------
+ * Replaces  Matrix<R>::checked_mul_vec / try_mul_vec / Mul<&[R]>  with R = RqNTT
+ *           (linear_algebra/src/matrix.rs:168-183, 199-205).
+ * rows[i] points at row i: ncols NTT-form elements (each row is its own allocation, as in
+ * Matrix.vals: Vec<Vec<R>>, matrix.rs:17-21); v holds v_limbs limbs; out receives nrows elements.
+ * ncols * limbs/element != v_limbs  ->  SR_ERR_BAD_LENGTH (the reference returns None /
+ * AlgebraError::DifferentLengths(ncols, v.len()), matrix.rs:169-171,180-183). */
+int sr_matvec(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols,
+              const uint64_t* v, size_t v_limbs, uint64_t* out, int loc);
+
+/* Column-sharded commitment, one rank's share: the same product over this rank's
+ * columns only, leaving nrows partial elements in `partial_out` (device or host).  The partials of
+ * all ranks are gathered by the caller (NCCL all-gather of raw limbs) and summed mod p on rank 0: */
+int sr_matvec_partial(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols,
+                      const uint64_t* v, size_t v_limbs, uint64_t* partial_out, int loc);
+/* out[i] = sum_r gathered[r * nrows + i]  (mod p, NTT form; an NCCL sum cannot reduce mod p). */
+int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t nranks, size_t nrows,
+                       uint64_t* out, int loc);
+
+/* ---- per-prime entry points (what each model module binds) --------------------------------- */
+#define SR_DECLARE_RING(tag)                                                                          \
+    int sr_##tag##_crt_batch(sr_ctx* ctx, uint64_t* buf, size_t n_limbs, int loc);                   \
+    int sr_##tag##_icrt_batch(sr_ctx* ctx, uint64_t* buf, size_t n_limbs, int loc);                  \
+    int sr_##tag##_ntt_mul_batch(sr_ctx* ctx, uint64_t* a_inout, const uint64_t* b, size_t n_limbs,  \
+                                 int loc);                                                            \
+    int sr_##tag##_ring_mul_batch(sr_ctx* ctx, const uint64_t* a, const uint64_t* b, uint64_t* out,  \
+                                  size_t n_limbs, int loc);                                           \
+    int sr_##tag##_matvec(sr_ctx* ctx, const uint64_t* const* rows, size_t nrows, size_t ncols,      \
+                          const uint64_t* v, size_t v_limbs, uint64_t* out, int loc);
+
+SR_DECLARE_RING(gl) /* goldilocks::{RqPoly,RqNTT},  models/goldilocks/mod.rs:31-32,100-118,151 */
+SR_DECLARE_RING(bb) /* babybear::{RqPoly,RqNTT},    models/babybear/mod.rs:30-31,112-130,163   */
+SR_DECLARE_RING(sp) /* stark_prime::{RqPoly,RqNTT}, models/stark_prime/mod.rs:29-30,49-67,97   */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARK_RINGS_CUDA_H */

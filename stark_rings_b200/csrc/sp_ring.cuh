@@ -1,0 +1,212 @@
+// Starknet-prime ring F_p[X]/(X^16 + 1), p = 2^251 + 17 * 2^192 + 1: per-element transforms.
+//
+// Mirrors (reference, crates/ring/src/cyclotomic_ring/models/stark_prime/):
+//   ntt.rs:121-235  serial_stark_prime_crt_in_place   -> sp::crt
+//   ntt.rs:245-346  serial_stark_prime_icrt_in_place  -> sp::icrt
+//   ntt_form.rs:159-175 with BaseCRTField = Fq        -> sp::mont_mul per slot
+//
+// A field element is ark-ff Fp256<MontBackend<_,4>>: 4 little-endian u64 limbs of x * 2^256 mod p,
+// handled here as 8 little-endian 32-bit limbs.  Multiplication is Montgomery (CIOS, 32-bit
+// limbs).  p = 1 (mod 2^32), so -p^-1 mod 2^32 = 0xFFFFFFFF and the reduction multiplier is just
+// m = -t0; p has three non-zero 32-bit limbs (limb 0 = 1, limb 6 = 0x11, limb 7 = 0x08000000), so
+// adding m * p costs two multiply-adds per round instead of eight.
+#pragma once
+#include "sr_common.cuh"
+#include "sr_consts_gen.cuh"
+
+namespace sr {
+namespace sp {
+
+constexpr int D = 16;   // coefficients per element
+constexpr int L = 8;    // 32-bit limbs per coefficient
+constexpr u32 P6 = 0x00000011u, P7 = 0x08000000u;  // p = 1 + P6 * 2^192 + P7 * 2^224
+
+struct Fe {
+    u32 v[L];
+};
+
+constexpr u32 p_limb(int i) { return i == 0 ? 1u : i == 6 ? P6 : i == 7 ? P7 : 0u; }
+
+struct RootTable {
+    u32 w[32][8];
+};
+constexpr RootTable ROOTS_MONT = {SR_SP_ROOTS_MONT};
+constexpr u32 root_limb(int k, int i) { return ROOTS_MONT.w[k][i]; }
+// WHICH = 0: 1/16; WHICH = 1: ROOTS_OF_UNITY_32[24] / 16 (ntt.rs:51-55), Montgomery form
+constexpr u32 scale_limb(int which, int i) {
+    constexpr u32 a[8] = SR_SP_SIXTEEN_INV_MONT;
+    constexpr u32 b[8] = SR_SP_SIXTEEN_INV_W24_MONT;
+    return which == 0 ? a[i] : b[i];
+}
+
+// r = a + b mod p (inputs canonical)
+SR_HD void add(Fe& r, const Fe& a, const Fe& b) {
+    u32 s[L], d[L];
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        c += (u64)a.v[i] + b.v[i];
+        s[i] = (u32)c;
+        c >>= 32;
+    }
+    // d = s - p; keep d if no borrow (s >= p).  a + b < 2p < 2^253: no carry out of s.
+    u64 br = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        u64 t = (u64)s[i] - p_limb(i) - br;
+        d[i] = (u32)t;
+        br = (t >> 63) & 1;
+    }
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = br ? s[i] : d[i];
+}
+// r = a - b mod p
+SR_HD void sub(Fe& r, const Fe& a, const Fe& b) {
+    u32 d[L];
+    u64 br = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        u64 t = (u64)a.v[i] - b.v[i] - br;
+        d[i] = (u32)t;
+        br = (t >> 63) & 1;
+    }
+    // if borrowed add p back
+    u32 mask = (u32)0 - (u32)br;
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        c += (u64)d[i] + (p_limb(i) & mask);
+        r.v[i] = (u32)c;
+        c >>= 32;
+    }
+}
+
+// One CIOS round: t += a * bi; then t = (t + m p) / 2^32 with m = -t0.
+SR_HD void mont_round(u32 (&t)[L + 2], const u32 (&a)[L], u32 bi) {
+    u64 c = 0;
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+        c += (u64)a[j] * bi + t[j];
+        t[j] = (u32)c;
+        c >>= 32;
+    }
+    c += t[L];
+    t[L] = (u32)c;
+    t[L + 1] = (u32)(c >> 32);
+    u32 m = 0u - t[0];
+    c = (t[0] != 0) ? 1 : 0;  // t0 + m = 2^32 (or 0 when t0 = 0)
+#pragma unroll
+    for (int j = 1; j < L; j++) {
+        if (j == 6) c += (u64)m * P6;
+        if (j == 7) c += (u64)m * P7;
+        c += t[j];
+        t[j - 1] = (u32)c;
+        c >>= 32;
+    }
+    c += t[L];
+    t[L - 1] = (u32)c;
+    t[L] = t[L + 1] + (u32)(c >> 32);
+}
+// r = a * b * 2^-256 mod p (canonical output for canonical inputs)
+SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
+    u32 t[L + 2];
+#pragma unroll
+    for (int i = 0; i < L + 2; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) mont_round(t, a, b[i]);
+    // t < 2p: conditional subtraction
+    u32 d[L];
+    u64 br = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+        u64 x = (u64)t[i] - p_limb(i) - br;
+        d[i] = (u32)x;
+        br = (x >> 63) & 1;
+    }
+    bool keep_t = br && (t[L] == 0);
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = keep_t ? t[i] : d[i];
+}
+SR_HD void mont_mul(Fe& r, const Fe& a, const Fe& b) { mont_mul_limbs(r, a.v, b.v); }
+
+// r = a * ROOTS_OF_UNITY_32[K] (constant in Montgomery form, limbs as immediates)
+template <int K>
+SR_HD void mulw(Fe& r, const Fe& a) {
+    constexpr u32 w[L] = {root_limb(K, 0), root_limb(K, 1), root_limb(K, 2), root_limb(K, 3),
+                          root_limb(K, 4), root_limb(K, 5), root_limb(K, 6), root_limb(K, 7)};
+    mont_mul_limbs(r, a.v, w);
+}
+template <int WHICH>
+SR_HD void mul_scale(Fe& r, const Fe& a) {
+    constexpr u32 w[L] = {scale_limb(WHICH, 0), scale_limb(WHICH, 1), scale_limb(WHICH, 2), scale_limb(WHICH, 3),
+                          scale_limb(WHICH, 4), scale_limb(WHICH, 5), scale_limb(WHICH, 6), scale_limb(WHICH, 7)};
+    mont_mul_limbs(r, a.v, w);
+}
+
+template <int I, int SPAN, int K>
+SR_HD void bfly(Fe (&c)[D]) {  // (a, b) <- (a + w b, a - w b)
+#pragma unroll
+    for (int i = 0; i < SPAN; i++) {
+        Fe t, a = c[I + i];
+        mulw<K>(t, c[I + SPAN + i]);
+        add(c[I + i], a, t);
+        sub(c[I + SPAN + i], a, t);
+    }
+}
+template <int I, int SPAN, int K>
+SR_HD void ibfly(Fe (&c)[D]) {  // (a, b) <- (a + b, w (a - b))
+#pragma unroll
+    for (int i = 0; i < SPAN; i++) {
+        Fe a = c[I + i], b = c[I + SPAN + i], d;
+        add(c[I + i], a, b);
+        sub(d, a, b);
+        mulw<K>(c[I + SPAN + i], d);
+    }
+}
+
+// ntt.rs:121-235
+SR_HD void crt(Fe (&c)[D]) {
+    bfly<0, 8, 8>(c);
+    bfly<0, 4, 4>(c);
+    bfly<8, 4, 12>(c);
+    bfly<0, 2, 2>(c);
+    bfly<4, 2, 10>(c);
+    bfly<8, 2, 6>(c);
+    bfly<12, 2, 14>(c);
+    bfly<0, 1, 1>(c);
+    bfly<2, 1, 9>(c);
+    bfly<4, 1, 5>(c);
+    bfly<6, 1, 13>(c);
+    bfly<8, 1, 3>(c);
+    bfly<10, 1, 11>(c);
+    bfly<12, 1, 7>(c);
+    bfly<14, 1, 15>(c);
+}
+// ntt.rs:245-346
+SR_HD void icrt(Fe (&c)[D]) {
+    ibfly<0, 1, 31>(c);
+    ibfly<2, 1, 23>(c);
+    ibfly<4, 1, 27>(c);
+    ibfly<6, 1, 19>(c);
+    ibfly<8, 1, 29>(c);
+    ibfly<10, 1, 21>(c);
+    ibfly<12, 1, 25>(c);
+    ibfly<14, 1, 17>(c);
+    ibfly<0, 2, 30>(c);
+    ibfly<4, 2, 22>(c);
+    ibfly<8, 2, 26>(c);
+    ibfly<12, 2, 18>(c);
+    ibfly<0, 4, 28>(c);
+    ibfly<8, 4, 20>(c);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        Fe a = c[i], b = c[8 + i], s, d;
+        add(s, a, b);
+        sub(d, a, b);
+        mul_scale<0>(c[i], s);
+        mul_scale<1>(c[8 + i], d);
+    }
+}
+
+}  // namespace sp
+}  // namespace sr

@@ -1,0 +1,460 @@
+// C ABI of libstarkrings_cuda.so (include/stark_rings_cuda.h): context, memory, dispatch, the
+// host-buffer pipeline.  No CPU fallback exists: every entry point either runs the sm_100a
+// kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/stark_rings_cuda.h"
+#include "sr_common.cuh"
+
+namespace sr {
+// per-ring launchers (bb_kernels.cu, gl_kernels.cu, sp_kernels.cu)
+cudaError_t bb_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms);
+cudaError_t gl_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms);
+cudaError_t sp_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms);
+// mat-vec (sr_matvec.cu): partial products of `ncols` columns -> nrows elements in out; uses
+// scratch (>= matvec_scratch_bytes).  Returns the number of kernels launched via *launches.
+size_t matvec_scratch_bytes(int ring, size_t nrows, int sms);
+cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
+                          u64* out, void* scratch, cudaStream_t st, int sms, int* launches);
+cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t nrows, u64* out,
+                          cudaStream_t st);
+}  // namespace sr
+
+using sr::u64;
+
+struct sr_ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;      // stream used for device-resident calls
+    cudaStream_t own_stream = nullptr;  // created by sr_init
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host pipeline
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    // host pipeline staging (device side), grown on demand
+    static constexpr int NBUF = 3;
+    void* stage[NBUF][3] = {};
+    size_t stage_bytes = 0;
+    cudaEvent_t ev_in[NBUF] = {}, ev_k[NBUF] = {}, ev_out[NBUF] = {};
+    // mat-vec scratch
+    void* mv_scratch = nullptr;
+    size_t mv_scratch_bytes = 0;
+    void* mv_rows = nullptr;  // device copy of the row-pointer table
+    size_t mv_rows_cap = 0;
+};
+
+namespace {
+
+int fail(sr_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+int cuda_fail(sr_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, SR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                               \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
+    } while (0)
+
+size_t elem_limbs(int ring) {
+    switch (ring) {
+    case SR_GOLDILOCKS: return 24;
+    case SR_BABYBEAR: return 72;
+    case SR_STARK: return 64;
+    }
+    return 0;
+}
+
+cudaError_t launch(int ring, int op, const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms) {
+    switch (ring) {
+    case SR_GOLDILOCKS: return sr::gl_launch(op, a, b, out, n, st, sms);
+    case SR_BABYBEAR: return sr::bb_launch(op, a, b, out, n, st, sms);
+    case SR_STARK: return sr::sp_launch(op, a, b, out, n, st, sms);
+    }
+    return cudaErrorInvalidValue;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int ensure_stage(sr_ctx* ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return SR_OK;
+    for (int i = 0; i < sr_ctx::NBUF; i++)
+        for (int j = 0; j < 3; j++) {
+            if (ctx->stage[i][j]) cudaFree(ctx->stage[i][j]);
+            ctx->stage[i][j] = nullptr;
+        }
+    ctx->stage_bytes = 0;
+    for (int i = 0; i < sr_ctx::NBUF; i++)
+        for (int j = 0; j < 2; j++) CU(cudaMalloc(&ctx->stage[i][j], bytes));
+    ctx->stage_bytes = bytes;
+    return SR_OK;
+}
+
+// Host-buffer path: the batch is cut into chunks that flow through a 3-deep ring of device
+// buffers; H2D of chunk i+1, the kernel of chunk i and D2H of chunk i-1 overlap on three streams.
+int batch_host(sr_ctx* ctx, int ring, int op, const u64* a, const u64* b, u64* out, size_t n) {
+    const size_t w = elem_limbs(ring), ebytes = w * 8;
+    const bool two = (op == sr::OP_NTT_MUL || op == sr::OP_RING_MUL);
+    size_t chunk_elems = ((size_t)64 << 20) / ebytes;  // 64 MiB per operand per chunk
+    if (chunk_elems > n) chunk_elems = n;
+    if (chunk_elems == 0) return SR_OK;
+    int rc = ensure_stage(ctx, chunk_elems * ebytes);
+    if (rc) return rc;
+    const size_t nchunks = (n + chunk_elems - 1) / chunk_elems;
+    for (size_t c = 0; c < nchunks; c++) {
+        const int s = (int)(c % sr_ctx::NBUF);
+        const size_t e0 = c * chunk_elems, ne = (n - e0 < chunk_elems) ? n - e0 : chunk_elems;
+        u64* dA = (u64*)ctx->stage[s][0];
+        u64* dB = (u64*)ctx->stage[s][1];
+        // the slot is free once the D2H of the chunk that used it last has finished
+        if (c >= (size_t)sr_ctx::NBUF) CU(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_out[s], 0));
+        CU(cudaMemcpyAsync(dA, a + e0 * w, ne * ebytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        if (two) CU(cudaMemcpyAsync(dB, b + e0 * w, ne * ebytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        CU(cudaEventRecord(ctx->ev_in[s], ctx->copy_in));
+        CU(cudaStreamWaitEvent(ctx->own_stream, ctx->ev_in[s], 0));
+        CU(launch(ring, op, dA, dB, dA, ne, ctx->own_stream, ctx->sms));
+        ctx->launches++;
+        CU(cudaEventRecord(ctx->ev_k[s], ctx->own_stream));
+        CU(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[s], 0));
+        CU(cudaMemcpyAsync(out + e0 * w, dA, ne * ebytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+        CU(cudaEventRecord(ctx->ev_out[s], ctx->copy_out));
+    }
+    CU(cudaStreamSynchronize(ctx->copy_out));
+    return SR_OK;
+}
+
+int batch(sr_ctx* ctx, int ring, int op, const u64* a, const u64* b, u64* out, size_t n_limbs, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (n_limbs % w != 0)
+        return fail(ctx, SR_ERR_BAD_LENGTH,
+                    "slice length " + std::to_string(n_limbs) + " is not a multiple of " + std::to_string(w));
+    if (n_limbs == 0) return SR_OK;
+    const bool two = (op == sr::OP_NTT_MUL || op == sr::OP_RING_MUL);
+    if (!a || !out || (two && !b)) return fail(ctx, SR_ERR_INVALID, "null buffer");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = n_limbs / w;
+    if (loc == SR_DEVICE) {
+        if (!aligned16(a) || !aligned16(out) || (two && !aligned16(b)))
+            return fail(ctx, SR_ERR_INVALID, "device buffers must be 16-byte aligned");
+        CU(launch(ring, op, a, b, out, n, ctx->stream, ctx->sms));
+        ctx->launches++;
+        return SR_OK;
+    }
+    if (loc == SR_HOST) return batch_host(ctx, ring, op, a, b, out, n);
+    return fail(ctx, SR_ERR_INVALID, "unknown loc");
+}
+
+int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, size_t ncols, const u64* v,
+                size_t v_limbs, u64* out, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (v_limbs % w != 0 || v_limbs / w != ncols)
+        return fail(ctx, SR_ERR_BAD_LENGTH,
+                    "DifferentLengths(" + std::to_string(ncols) + ", " + std::to_string(v_limbs / (w ? w : 1)) + ")");
+    if (nrows == 0) return SR_OK;
+    if (!rows || !out || (ncols && !v)) return fail(ctx, SR_ERR_INVALID, "null buffer");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
+    // scratch + row table
+    const size_t need = sr::matvec_scratch_bytes(ring, nrows, ctx->sms);
+    if (ctx->mv_scratch_bytes < need) {
+        if (ctx->mv_scratch) cudaFree(ctx->mv_scratch);
+        ctx->mv_scratch = nullptr;
+        ctx->mv_scratch_bytes = 0;
+        CU(cudaMalloc(&ctx->mv_scratch, need));
+        ctx->mv_scratch_bytes = need;
+    }
+    if (ctx->mv_rows_cap < nrows) {
+        if (ctx->mv_rows) cudaFree(ctx->mv_rows);
+        ctx->mv_rows = nullptr;
+        ctx->mv_rows_cap = 0;
+        CU(cudaMalloc(&ctx->mv_rows, nrows * sizeof(void*)));
+        ctx->mv_rows_cap = nrows;
+    }
+    int launches = 0;
+    if (loc == SR_DEVICE) {
+        for (size_t i = 0; i < nrows; i++)
+            if (!rows[i] || !aligned16(rows[i])) return fail(ctx, SR_ERR_INVALID, "row pointer null or misaligned");
+        CU(cudaMemcpyAsync(ctx->mv_rows, rows, nrows * sizeof(void*), cudaMemcpyHostToDevice, st));
+        CU(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, v, out, ctx->mv_scratch, st,
+                             ctx->sms, &launches));
+        ctx->launches += launches;
+        return SR_OK;
+    }
+    if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    // Host path: whole operands are copied to the device (a commitment matrix is normally kept
+    // resident with SR_DEVICE; this path exists for drop-in completeness).
+    const size_t row_bytes = ncols * w * 8;
+    std::vector<void*> drows(nrows, nullptr);
+    void* dv = nullptr;
+    void* dout = nullptr;
+    int rc = SR_OK;
+    auto cleanup = [&]() {
+        for (void* p : drows)
+            if (p) cudaFree(p);
+        if (dv) cudaFree(dv);
+        if (dout) cudaFree(dout);
+    };
+#define CUX(call)                                   \
+    do {                                            \
+        cudaError_t e_ = (call);                    \
+        if (e_ != cudaSuccess) {                    \
+            rc = cuda_fail(ctx, e_, #call);         \
+            cleanup();                              \
+            return rc;                              \
+        }                                           \
+    } while (0)
+    CUX(cudaMalloc(&dout, nrows * w * 8));
+    if (ncols) {
+        CUX(cudaMalloc(&dv, row_bytes));
+        CUX(cudaMemcpyAsync(dv, v, row_bytes, cudaMemcpyHostToDevice, st));
+        for (size_t i = 0; i < nrows; i++) {
+            if (!rows[i]) { cleanup(); return fail(ctx, SR_ERR_INVALID, "null row pointer"); }
+            CUX(cudaMalloc(&drows[i], row_bytes));
+            CUX(cudaMemcpyAsync(drows[i], rows[i], row_bytes, cudaMemcpyHostToDevice, st));
+        }
+    }
+    CUX(cudaMemcpyAsync(ctx->mv_rows, drows.data(), nrows * sizeof(void*), cudaMemcpyHostToDevice, st));
+    CUX(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, (const u64*)dv, (u64*)dout,
+                          ctx->mv_scratch, st, ctx->sms, &launches));
+    ctx->launches += launches;
+    CUX(cudaMemcpyAsync(out, dout, nrows * w * 8, cudaMemcpyDeviceToHost, st));
+    CUX(cudaStreamSynchronize(st));
+#undef CUX
+    cleanup();
+    return SR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sr_version(void) { return "stark-rings-b200 0.1 (sm_100a)"; }
+
+size_t sr_elem_limbs(int ring) { return elem_limbs(ring); }
+
+int sr_init(int device, sr_ctx** out) {
+    if (!out) return SR_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) return SR_ERR_CUDA;  // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return SR_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SR_ERR_CUDA;
+    if (prop.major != 10) {
+        fprintf(stderr, "stark-rings-b200: device %d is sm_%d%d; this library carries sm_100a code only\n", device,
+                prop.major, prop.minor);
+        return SR_ERR_CUDA;
+    }
+    sr_ctx* ctx = new sr_ctx();
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreate(&ctx->t0) == cudaSuccess && cudaEventCreate(&ctx->t1) == cudaSuccess;
+    for (int i = 0; ok && i < sr_ctx::NBUF; i++)
+        ok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        delete ctx;
+        return SR_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SR_OK;
+}
+
+int sr_destroy(sr_ctx* ctx) {
+    if (!ctx) return SR_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < sr_ctx::NBUF; i++) {
+        for (int j = 0; j < 3; j++)
+            if (ctx->stage[i][j]) cudaFree(ctx->stage[i][j]);
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->mv_scratch) cudaFree(ctx->mv_scratch);
+    if (ctx->mv_rows) cudaFree(ctx->mv_rows);
+    if (ctx->t0) cudaEventDestroy(ctx->t0);
+    if (ctx->t1) cudaEventDestroy(ctx->t1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+    return SR_OK;
+}
+
+const char* sr_last_error(sr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sr_set_stream(sr_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SR_OK;
+}
+
+int sr_sync(sr_ctx* ctx) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->stream != ctx->own_stream) CU(cudaStreamSynchronize(ctx->own_stream));
+    return SR_OK;
+}
+
+uint64_t sr_kernel_launches(sr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sr_dev_alloc(sr_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 16);
+    if (e == cudaErrorMemoryAllocation) return fail(ctx, SR_ERR_NOMEM, "cudaMalloc: out of device memory");
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+    return SR_OK;
+}
+int sr_dev_free(sr_ctx* ctx, void* dptr) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(dptr));
+    return SR_OK;
+}
+int sr_host_alloc(sr_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 16);
+    if (e == cudaErrorMemoryAllocation) return fail(ctx, SR_ERR_NOMEM, "cudaMallocHost: out of memory");
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMallocHost");
+    return SR_OK;
+}
+int sr_host_free(sr_ctx* ctx, void* hptr) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaFreeHost(hptr));
+    return SR_OK;
+}
+int sr_h2d(sr_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SR_OK;
+}
+int sr_d2h(sr_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SR_OK;
+}
+
+int sr_timer_start(sr_ctx* ctx) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->t0, ctx->stream));
+    return SR_OK;
+}
+int sr_timer_stop(sr_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->t1, ctx->stream));
+    CU(cudaEventSynchronize(ctx->t1));
+    CU(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return SR_OK;
+}
+
+int sr_crt_batch(sr_ctx* ctx, int ring, uint64_t* buf, size_t n_limbs, int loc) {
+    return batch(ctx, ring, sr::OP_CRT, buf, nullptr, buf, n_limbs, loc);
+}
+int sr_icrt_batch(sr_ctx* ctx, int ring, uint64_t* buf, size_t n_limbs, int loc) {
+    return batch(ctx, ring, sr::OP_ICRT, buf, nullptr, buf, n_limbs, loc);
+}
+int sr_ntt_mul_batch(sr_ctx* ctx, int ring, uint64_t* a, const uint64_t* b, size_t n_limbs, int loc) {
+    return batch(ctx, ring, sr::OP_NTT_MUL, a, b, a, n_limbs, loc);
+}
+int sr_ring_mul_batch(sr_ctx* ctx, int ring, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n_limbs,
+                      int loc) {
+    return batch(ctx, ring, sr::OP_RING_MUL, a, b, out, n_limbs, loc);
+}
+
+int sr_matvec(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v,
+              size_t v_limbs, uint64_t* out, int loc) {
+    return matvec_impl(ctx, ring, rows, nrows, ncols, v, v_limbs, out, loc);
+}
+int sr_matvec_partial(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols,
+                      const uint64_t* v, size_t v_limbs, uint64_t* partial_out, int loc) {
+    return matvec_impl(ctx, ring, rows, nrows, ncols, v, v_limbs, partial_out, loc);
+}
+int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t nranks, size_t nrows, uint64_t* out,
+                       int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (nrows == 0) return SR_OK;
+    if (!gathered || !out || nranks == 0) return fail(ctx, SR_ERR_INVALID, "null buffer / zero ranks");
+    CU(cudaSetDevice(ctx->device));
+    if (loc == SR_DEVICE) {
+        CU(sr::modsum_launch(ring, gathered, nranks, nrows, out, ctx->stream));
+        ctx->launches++;
+        return SR_OK;
+    }
+    if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    void *dg = nullptr, *dout = nullptr;
+    const size_t gbytes = nranks * nrows * w * 8, obytes = nrows * w * 8;
+    cudaError_t e = cudaMalloc(&dg, gbytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, obytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dg, gathered, gbytes, cudaMemcpyHostToDevice, ctx->own_stream);
+    if (e == cudaSuccess) e = sr::modsum_launch(ring, (const u64*)dg, nranks, nrows, (u64*)dout, ctx->own_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, ctx->own_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);
+    if (dg) cudaFree(dg);
+    if (dout) cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "sr_modsum_partials");
+    ctx->launches++;
+    return SR_OK;
+}
+
+#define SR_DEFINE_RING(tag, RING)                                                                             \
+    int sr_##tag##_crt_batch(sr_ctx* c, uint64_t* buf, size_t n, int loc) { return sr_crt_batch(c, RING, buf, n, loc); }   \
+    int sr_##tag##_icrt_batch(sr_ctx* c, uint64_t* buf, size_t n, int loc) { return sr_icrt_batch(c, RING, buf, n, loc); } \
+    int sr_##tag##_ntt_mul_batch(sr_ctx* c, uint64_t* a, const uint64_t* b, size_t n, int loc) {             \
+        return sr_ntt_mul_batch(c, RING, a, b, n, loc);                                                       \
+    }                                                                                                         \
+    int sr_##tag##_ring_mul_batch(sr_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n,  \
+                                  int loc) {                                                                  \
+        return sr_ring_mul_batch(c, RING, a, b, out, n, loc);                                                 \
+    }                                                                                                         \
+    int sr_##tag##_matvec(sr_ctx* c, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v, \
+                          size_t v_limbs, uint64_t* out, int loc) {                                           \
+        return sr_matvec(c, RING, rows, nrows, ncols, v, v_limbs, out, loc);                                  \
+    }
+
+SR_DEFINE_RING(gl, SR_GOLDILOCKS)
+SR_DEFINE_RING(bb, SR_BABYBEAR)
+SR_DEFINE_RING(sp, SR_STARK)
+
+}  // extern "C"

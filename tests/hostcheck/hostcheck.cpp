@@ -1,0 +1,68 @@
+// TEST INFRASTRUCTURE: compiles the kernels' __host__ __device__ per-element arithmetic for the
+// CPU so that it can be checked against the oracle without a GPU (tests/test_hostcheck.py).
+// Not part of the product; libstarkrings_cuda.so has no CPU path.
+#include <cstdint>
+#include <cstring>
+
+#include "bb_ring.cuh"
+#include "gl_ring.cuh"
+#include "sp_ring.cuh"
+
+using namespace sr;
+
+extern "C" {
+
+void hc_bb_crt(uint64_t* e) {
+    u32 c[72];
+    for (int i = 0; i < 72; i++) c[i] = (u32)e[i];
+    bb::crt(c);
+    for (int i = 0; i < 72; i++) e[i] = c[i];
+}
+void hc_bb_icrt(uint64_t* e) {
+    u32 c[72];
+    for (int i = 0; i < 72; i++) c[i] = (u32)e[i];
+    bb::icrt(c);
+    for (int i = 0; i < 72; i++) e[i] = c[i];
+}
+void hc_bb_ntt_mul(uint64_t* a, const uint64_t* b) {
+    u32 x[72], y[72];
+    for (int i = 0; i < 72; i++) { x[i] = (u32)a[i]; y[i] = (u32)b[i]; }
+    bb::ntt_mul(x, y);
+    for (int i = 0; i < 72; i++) a[i] = x[i];
+}
+void hc_bb_ring_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    u32 x[72], y[72];
+    for (int i = 0; i < 72; i++) { x[i] = (u32)a[i]; y[i] = (u32)b[i]; }
+    bb::crt_stages(x);
+    bb::crt_stages(y);
+    bb::fused_mul_icrt(y, x);
+    for (int i = 0; i < 72; i++) out[i] = y[i];
+}
+
+
+void hc_gl_crt(uint64_t* e) { u64 c[24]; memcpy(c, e, 192); gl::crt(c); memcpy(e, c, 192); }
+void hc_gl_icrt(uint64_t* e) { u64 c[24]; memcpy(c, e, 192); gl::icrt(c); memcpy(e, c, 192); }
+void hc_gl_ntt_mul(uint64_t* a, const uint64_t* b) {
+    u64 x[24], y[24]; memcpy(x, a, 192); memcpy(y, b, 192);
+    gl::ntt_mul(x, y); memcpy(a, x, 192);
+}
+void hc_gl_ring_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    u64 x[24], y[24]; memcpy(x, a, 192); memcpy(y, b, 192);
+    gl::crt_stages(x); gl::crt_stages(y); gl::fused_mul_icrt(y, x); memcpy(out, y, 192);
+}
+
+void hc_sp_crt(uint64_t* e) { sp::Fe c[16]; memcpy(c, e, 512); sp::crt(c); memcpy(e, c, 512); }
+void hc_sp_icrt(uint64_t* e) { sp::Fe c[16]; memcpy(c, e, 512); sp::icrt(c); memcpy(e, c, 512); }
+void hc_sp_ntt_mul(uint64_t* a, const uint64_t* b) {
+    sp::Fe x[16], y[16]; memcpy(x, a, 512); memcpy(y, b, 512);
+    for (int i = 0; i < 16; i++) sp::mont_mul(x[i], x[i], y[i]);
+    memcpy(a, x, 512);
+}
+void hc_sp_ring_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    sp::Fe x[16], y[16]; memcpy(x, a, 512); memcpy(y, b, 512);
+    sp::crt(x); sp::crt(y);
+    for (int i = 0; i < 16; i++) sp::mont_mul(y[i], y[i], x[i]);
+    sp::icrt(y); memcpy(out, y, 512);
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes -> libstarkrings_cuda.so), against
+the oracle on identical seeded inputs.  Bit-exact (integer arithmetic): np.array_equal everywhere."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as C
+from oracle import ref_py as O
+from tests.util import WORDS, rand_raw
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["goldilocks", "babybear", "stark_prime"]
+
+
+@pytest.fixture(scope="module")
+def S():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import stark_rings_b200 as S
+    S.default_context(0)  # raises if the extension cannot drive the GPU
+    return S
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(a.view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("n", [1, 2, 63, 129, 1000, 4099])
+def test_crt_icrt_device(S, name, n):
+    cfg = S.CONFIGS[name]
+    a = rand_raw(name, n, 100 + n)
+    want = C.crt(name, a.copy(), threads=8)
+    d = dev(a)
+    cfg.crt_batch(d)
+    assert np.array_equal(host(d), want)
+    cfg.icrt_batch(d)
+    assert np.array_equal(host(d), a)
+    # icrt of arbitrary data, too
+    want_i = C.icrt(name, a.copy(), threads=8)
+    d = dev(a)
+    cfg.icrt_batch(d)
+    assert np.array_equal(host(d), want_i)
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("n", [1, 129, 2050])
+def test_ntt_mul_and_ring_mul_device(S, name, n):
+    cfg = S.CONFIGS[name]
+    a, b = rand_raw(name, n, 200 + n), rand_raw(name, n, 300 + n)
+    w = WORDS[name]
+    if n >= 3:
+        b[: 2 * w] = a[w: 3 * w]  # 0 * (p-1), (p-1) * random
+    want_nm = C.ntt_mul(name, a.copy(), b.copy(), threads=8)
+    da, db = dev(a), dev(b)
+    cfg.ntt_mul_batch(da, db)
+    assert np.array_equal(host(da), want_nm)
+    assert np.array_equal(host(db), b)
+    want_rm = C.ring_mul(name, a, b, threads=8)
+    da = dev(a)
+    out = cfg.ring_mul_batch(da, db)
+    assert np.array_equal(host(out), want_rm)
+    assert np.array_equal(host(da), a)
+    # aliasing: out = a
+    cfg.ring_mul_batch(da, db, out=da)
+    assert np.array_equal(host(da), want_rm)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_host_buffers_pipeline(S, name):
+    """SR_HOST path: chunked H2D -> kernel -> D2H; n chosen to span several 64 MiB chunks."""
+    cfg = S.CONFIGS[name]
+    n = (3 * (64 << 20)) // (WORDS[name] * 8) + 77
+    a, b = rand_raw(name, n, 7), rand_raw(name, n, 8)
+    a0 = a.copy()
+    out = cfg.ring_mul_batch(a, b)
+    assert np.array_equal(a, a0)
+    # sample-check against the oracle (full check would take the CPU minutes)
+    w = WORDS[name]
+    idx = np.r_[0:64, n // 2:n // 2 + 64, n - 64:n]
+    sel = lambda x: np.concatenate([x[i * w:(i + 1) * w] for i in idx])
+    assert np.array_equal(sel(out), C.ring_mul(name, sel(a), sel(b), threads=8))
+    # whole-buffer property: crt then icrt is the identity
+    cfg.crt_batch(a)
+    assert not np.array_equal(a, a0)
+    cfg.icrt_batch(a)
+    assert np.array_equal(a, a0)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_golden_and_kats_on_device(S, name, golden):
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    g = golden(name)
+    for kat in g["crt_kats"]:
+        coeffs = [int(x) for x in kat["coeffs"]]
+        raw = np.array(O.to_raw(M, coeffs), dtype=np.uint64)
+        p = S.RqPoly(cfg, dev(raw))
+        ntt = p.crt()
+        got = O.from_raw(M, host(ntt.data).tolist())
+        key = "evaluations" if name == "stark_prime" else "slot_remainders"
+        assert M.dehomogenize(got) == [int(x) for x in kat[key]]
+        back = ntt.icrt()
+        assert O.from_raw(M, host(back.data).tolist()) == coeffs
+    gd = golden(name + "_derived")
+    for case in gd["cases"]:
+        a = np.array([int(x) for x in case["a_raw"]], dtype=np.uint64)
+        b = np.array(O.to_raw(M, [int(x) for x in case["b"]]), dtype=np.uint64)
+        prod = S.RqPoly(cfg, dev(a)) * S.RqPoly(cfg, dev(b))
+        assert host(prod.data).tolist() == [int(x) for x in case["ring_mul_raw"]]
+        assert host(cfg.crt(dev(a))).tolist() == [int(x) for x in case["crt_a_raw"]]
+    # crt(ONE) == ONE (models/*/mod.rs test_crt_one)
+    one = np.array(O.to_raw(M, [1] + [0] * (M.D - 1)), dtype=np.uint64)
+    ntt_one = []
+    for _ in range(M.D // M.d):
+        ntt_one += [1] + [0] * (M.d - 1)
+    assert host(cfg.crt(dev(one))).tolist() == O.to_raw(M, ntt_one)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_length_errors_and_empty(S, name):
+    cfg = S.CONFIGS[name]
+    import torch
+    bad = torch.zeros(cfg.limbs + 1, dtype=torch.int64, device="cuda")
+    with pytest.raises(S.LengthPanic):
+        cfg.crt_batch(bad)
+    with pytest.raises(S.LengthPanic):
+        cfg.crt_in_place(torch.zeros(2 * cfg.limbs, dtype=torch.int64, device="cuda"))
+    with pytest.raises(S.LengthPanic):
+        cfg.icrt_batch(np.zeros(cfg.limbs - 1, dtype=np.uint64))
+    empty = torch.zeros(0, dtype=torch.int64, device="cuda")
+    cfg.crt_batch(empty)
+    cfg.ring_mul_batch(empty, empty)
+    assert cfg.crt_batch(np.zeros(0, dtype=np.uint64)).size == 0
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("kappa,m", [(1, 1), (3, 7), (4, 1000), (5, 2049), (9, 300)])
+def test_matvec_device(S, name, kappa, m):
+    cfg = S.CONFIGS[name]
+    rows = [rand_raw(name, m, 1000 + 17 * i + m) for i in range(kappa)]
+    v = rand_raw(name, m, 999 + m)
+    want = C.matvec(name, rows, v, threads=8)
+    A = S.Matrix([S.RqNTT(cfg, dev(r)) for r in rows])
+    y = A.try_mul_vec(S.RqNTT(cfg, dev(v)))
+    assert np.array_equal(host(y.data), want)
+    # host buffers
+    Ah = S.Matrix([S.RqNTT(cfg, r) for r in rows])
+    yh = Ah @ S.RqNTT(cfg, v)
+    assert np.array_equal(yh.data, want)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_matvec_length_mismatch(S, name):
+    """matrix.rs:232-243: a too-short vector -> checked None / try Err(DifferentLengths)."""
+    cfg = S.CONFIGS[name]
+    rows = [rand_raw(name, 3, i) for i in range(2)]
+    A = S.Matrix([S.RqNTT(cfg, dev(r)) for r in rows])
+    v = S.RqNTT(cfg, dev(rand_raw(name, 2, 5)))
+    assert A.checked_mul_vec(v) is None
+    with pytest.raises(S.DifferentLengths) as ei:
+        A.try_mul_vec(v)
+    assert ei.value.lengths == (3, 2)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_sharded_commit_single_process(S, name):
+    """Column sharding emulated on one GPU: partials of G column shards, modular sum == full product."""
+    import ctypes
+    import torch
+    from stark_rings_b200 import _lib as L
+    cfg = S.CONFIGS[name]
+    kappa, m, G = 4, 1030, 4
+    rows = [rand_raw(name, m, 40 + i) for i in range(kappa)]
+    v = rand_raw(name, m, 50)
+    want = C.matvec(name, rows, v, threads=8)
+    w = WORDS[name]
+    parts = []
+    for r in range(G):
+        lo, hi = m * r // G, m * (r + 1) // G
+        A = S.Matrix([S.RqNTT(cfg, dev(x[lo * w:hi * w].copy())) for x in rows])
+        parts.append(A.partial_mul_vec(S.RqNTT(cfg, dev(v[lo * w:hi * w].copy()))).data)
+    gathered = torch.cat(parts)
+    out = torch.empty(kappa * w, dtype=torch.int64, device="cuda")
+    c = S.default_context(0)
+    c.check(L.lib.sr_modsum_partials(c.h, cfg.ring_id, ctypes.c_void_p(gathered.data_ptr()), G, kappa,
+                                     ctypes.c_void_p(out.data_ptr()), L.SR_DEVICE), "modsum")
+    assert np.array_equal(host(out), want)
+
+
+@pytest.mark.parametrize("name,n", [("goldilocks", 1 << 20), ("babybear", 1 << 19), ("stark_prime", 1 << 18)])
+def test_large_batch_properties(S, name, n):
+    """Size-independent properties at large n: round trip, commutativity, multiplication by ONE,
+    distributivity over a sampled oracle check."""
+    import torch
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    a, b = rand_raw(name, n, 1), rand_raw(name, n, 2)
+    da, db = dev(a), dev(b)
+    ab = cfg.ring_mul_batch(da, db)
+    ba = cfg.ring_mul_batch(db, da)
+    assert torch.equal(ab, ba)
+    t = da.clone()
+    cfg.crt_batch(t)
+    cfg.icrt_batch(t)
+    assert torch.equal(t, da)
+    one = np.tile(np.array(O.to_raw(M, [1] + [0] * (M.D - 1)), dtype=np.uint64), n)
+    assert torch.equal(cfg.ring_mul_batch(da, dev(one)), da)
+    w = WORDS[name]
+    idx = np.r_[0:32, n - 32:n]
+    sel = lambda x: np.concatenate([x[i * w:(i + 1) * w] for i in idx])
+    assert np.array_equal(sel(host(ab)), C.ring_mul(name, sel(a), sel(b), threads=8))
