@@ -53,7 +53,8 @@ int sr_init(int device, sr_ctx** out);
 int sr_destroy(sr_ctx* ctx);
 const char* sr_last_error(sr_ctx* ctx);       /* message of the last failing call on ctx */
 const char* sr_version(void);
-int sr_set_stream(sr_ctx* ctx, void* cuda_stream); /* use a caller-owned cudaStream_t for device calls */
+int sr_set_stream(sr_ctx* ctx, void* cuda_stream); /* enqueue SR_DEVICE calls on this cudaStream_t (NULL = default stream) */
+int sr_reset_stream(sr_ctx* ctx);                  /* back to the context's own non-blocking stream */
 int sr_sync(sr_ctx* ctx);
 size_t sr_elem_limbs(int ring);               /* 24 / 72 / 64; 0 for an unknown ring */
 uint64_t sr_kernel_launches(sr_ctx* ctx);     /* kernels launched by this context so far */

@@ -308,7 +308,14 @@ const char* sr_last_error(sr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null c
 int sr_set_stream(sr_ctx* ctx, void* cuda_stream) {
     if (!ctx) return SR_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;  // NULL is CUDA's (legacy) default stream
+    return SR_OK;
+}
+
+int sr_reset_stream(sr_ctx* ctx) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->stream = ctx->own_stream;
     return SR_OK;
 }
 

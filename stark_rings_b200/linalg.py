@@ -51,6 +51,8 @@ class Matrix:
             out = np.empty(self.nrows * cfg.limbs, dtype=np.uint64)
         po = _ptr_loc(out)[0]
         c = self.ctx or v.ctx or default_context(0 if dev is None else dev)
+        if dev is not None:
+            c.use_torch_stream()
         rc = fn(c.h, cfg.ring_id, ptrs, self.nrows, self.ncols, pv, nv, po, loc)
         if rc == L.SR_ERR_BAD_LENGTH:
             return None

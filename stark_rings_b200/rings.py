@@ -65,9 +65,13 @@ class Context:
         self.check(L.lib.sr_sync(self.h), "sr_sync")
 
     def use_torch_stream(self):
-        """Enqueue device-resident calls on torch's current stream (so torch.cuda.Event sees them)."""
-        s = torch.cuda.current_stream(self.device)
-        self.check(L.lib.sr_set_stream(self.h, ctypes.c_void_p(s.cuda_stream)), "sr_set_stream")
+        """Enqueue device-resident calls on torch's current stream: they are then ordered with the
+        surrounding torch operations and visible to torch.cuda.Event.  Called automatically whenever
+        a CUDA tensor is handed to this package."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if s != getattr(self, "_stream", -1):
+            self.check(L.lib.sr_set_stream(self.h, ctypes.c_void_p(s)), "sr_set_stream")
+            self._stream = s
 
     @property
     def kernel_launches(self) -> int:
@@ -120,7 +124,10 @@ class RingConfig:
         return "<RingConfig %s D=%d N=%d>" % (self.name, self.D, self.N)
 
     def _ctx(self, device, ctx):
-        return ctx or default_context(0 if device is None else device)
+        c = ctx or default_context(0 if device is None else device)
+        if device is not None:
+            c.use_torch_stream()
+        return c
 
     def _unary(self, fn_name, buf, single, ctx):
         p, n, loc, dev = _ptr_loc(buf)
