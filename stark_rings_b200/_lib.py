@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libstarkrings_cuda.so")
+LIB_PATH = os.environ.get("STARK_RINGS_LIB") or os.path.join(HERE, "libstarkrings_cuda.so")  # override: tuning builds
 
 SR_OK, SR_ERR_BAD_LENGTH, SR_ERR_CUDA, SR_ERR_INVALID, SR_ERR_NOMEM = 0, 1, 2, 3, 4
 SR_GOLDILOCKS, SR_BABYBEAR, SR_STARK = 0, 1, 2

@@ -10,6 +10,7 @@ struct BBPolicy {
     static constexpr int RING = RING_BB;
     static constexpr int WORDS64 = 72;
     static constexpr int CHUNKS = 36;  // 16-byte chunks per element in HBM
+    static constexpr int STAGE_UNROLL = 18;  // loads in flight per thread while staging
     static constexpr int ROW = 76;     // words per shared-memory row
     static constexpr int NREG = 72;
 

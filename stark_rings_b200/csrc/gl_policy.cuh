@@ -9,6 +9,7 @@ struct GLPolicy {
     static constexpr int RING = RING_GL;
     static constexpr int WORDS64 = 24;
     static constexpr int CHUNKS = 12;
+    static constexpr int STAGE_UNROLL = 12;  // loads in flight per thread while staging
     static constexpr int ROW = 52;
 
     SR_D static void put(u32* row, int j, uint4 v) { *reinterpret_cast<uint4*>(row + 4 * j) = v; }

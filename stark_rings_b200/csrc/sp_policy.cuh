@@ -11,6 +11,7 @@ struct SPPolicy {
     static constexpr int RING = RING_SP;
     static constexpr int WORDS64 = 64;
     static constexpr int CHUNKS = 32;
+    static constexpr int STAGE_UNROLL = 16;  // loads in flight per thread while staging
     static constexpr int ROW = 132;
 
     SR_D static void put(u32* row, int j, uint4 v) { *reinterpret_cast<uint4*>(row + 4 * j) = v; }

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstring>
 
+#include "bb_half.cuh"
 #include "bb_ring.cuh"
 #include "gl_ring.cuh"
 #include "sp_ring.cuh"
@@ -39,6 +40,26 @@ void hc_bb_ring_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
     for (int i = 0; i < 72; i++) out[i] = y[i];
 }
 
+
+// two-threads-per-element formulation, both halves run in sequence
+void hc_bb_ring_mul_half(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    u32 ra[72], rb[72];
+    for (int i = 0; i < 72; i++) { ra[i] = (u32)a[i]; rb[i] = (u32)b[i]; }
+    u32 B[2][36], O[2][36];
+    for (int h = 0; h < 2; h++) {
+        const bb::HalfConsts K = bb::half_consts(h);
+        u32 A[36];
+        bb::half_crt(A, ra, K);
+        bb::half_crt(B[h], rb, K);
+        bb::half_slots(B[h], A, K);
+        bb::half_icrt_local(B[h], K);
+    }
+    for (int h = 0; h < 2; h++) {
+        const bb::HalfConsts K = bb::half_consts(h);
+        bb::half_final(O[h], B[h], B[1 - h], K);
+        for (int i = 0; i < 36; i++) out[36 * h + i] = O[h][i];
+    }
+}
 
 void hc_gl_crt(uint64_t* e) { u64 c[24]; memcpy(c, e, 192); gl::crt(c); memcpy(e, c, 192); }
 void hc_gl_icrt(uint64_t* e) { u64 c[24]; memcpy(c, e, 192); gl::icrt(c); memcpy(e, c, 192); }

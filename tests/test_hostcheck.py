@@ -58,3 +58,7 @@ def test_elementwise_against_oracle(hc, name, tag):
         out = np.zeros(w, dtype=np.uint64)
         getattr(hc, "hc_%s_ring_mul" % tag)(_p(ea), _p(eb), _p(out))
         assert np.array_equal(out, want_rm[i * w:(i + 1) * w]), ("ring_mul", i)
+        if tag == "bb":  # two-threads-per-element formulation used by the fused kernel
+            out2 = np.zeros(w, dtype=np.uint64)
+            hc.hc_bb_ring_mul_half(_p(ea), _p(eb), _p(out2))
+            assert np.array_equal(out2, want_rm[i * w:(i + 1) * w]), ("ring_mul_half", i)
