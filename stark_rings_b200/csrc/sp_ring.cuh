@@ -41,6 +41,36 @@ constexpr u32 scale_limb(int which, int i) {
 
 // r = a + b mod p (inputs canonical)
 SR_HD void add(Fe& r, const Fe& a, const Fe& b) {
+#if defined(__CUDA_ARCH__)
+    u32 s[L], d[L], br;
+    asm volatile(
+        "add.cc.u32   %0, %8,  %16;\n\t"
+        "addc.cc.u32  %1, %9,  %17;\n\t"
+        "addc.cc.u32  %2, %10, %18;\n\t"
+        "addc.cc.u32  %3, %11, %19;\n\t"
+        "addc.cc.u32  %4, %12, %20;\n\t"
+        "addc.cc.u32  %5, %13, %21;\n\t"
+        "addc.cc.u32  %6, %14, %22;\n\t"
+        "addc.u32     %7, %15, %23;\n\t"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    asm volatile(
+        "sub.cc.u32   %0, %9,  1;\n\t"
+        "subc.cc.u32  %1, %10, 0;\n\t"
+        "subc.cc.u32  %2, %11, 0;\n\t"
+        "subc.cc.u32  %3, %12, 0;\n\t"
+        "subc.cc.u32  %4, %13, 0;\n\t"
+        "subc.cc.u32  %5, %14, 0;\n\t"
+        "subc.cc.u32  %6, %15, 0x11;\n\t"
+        "subc.cc.u32  %7, %16, 0x08000000;\n\t"
+        "subc.u32     %8, 0, 0;\n\t"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(br)
+        : "r"(s[0]), "r"(s[1]), "r"(s[2]), "r"(s[3]), "r"(s[4]), "r"(s[5]), "r"(s[6]), "r"(s[7]));
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = br ? s[i] : d[i];
+    return;
+#else
     u32 s[L], d[L];
     u64 c = 0;
 #pragma unroll
@@ -59,9 +89,41 @@ SR_HD void add(Fe& r, const Fe& a, const Fe& b) {
     }
 #pragma unroll
     for (int i = 0; i < L; i++) r.v[i] = br ? s[i] : d[i];
+#endif
 }
 // r = a - b mod p
 SR_HD void sub(Fe& r, const Fe& a, const Fe& b) {
+#if defined(__CUDA_ARCH__)
+    u32 d[L], br;
+    asm volatile(
+        "sub.cc.u32   %0, %9,  %17;\n\t"
+        "subc.cc.u32  %1, %10, %18;\n\t"
+        "subc.cc.u32  %2, %11, %19;\n\t"
+        "subc.cc.u32  %3, %12, %20;\n\t"
+        "subc.cc.u32  %4, %13, %21;\n\t"
+        "subc.cc.u32  %5, %14, %22;\n\t"
+        "subc.cc.u32  %6, %15, %23;\n\t"
+        "subc.cc.u32  %7, %16, %24;\n\t"
+        "subc.u32     %8, 0, 0;\n\t"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(br)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    // br = 0 or 0xFFFFFFFF: add p back when the subtraction borrowed
+    asm volatile(
+        "add.cc.u32   %0, %0, %8;\n\t"
+        "addc.cc.u32  %1, %1, 0;\n\t"
+        "addc.cc.u32  %2, %2, 0;\n\t"
+        "addc.cc.u32  %3, %3, 0;\n\t"
+        "addc.cc.u32  %4, %4, 0;\n\t"
+        "addc.cc.u32  %5, %5, 0;\n\t"
+        "addc.cc.u32  %6, %6, %9;\n\t"
+        "addc.u32     %7, %7, %10;\n\t"
+        : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7])
+        : "r"(br & 1u), "r"(br & P6), "r"(br & P7));
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = d[i];
+    return;
+#else
     u32 d[L];
     u64 br = 0;
 #pragma unroll
@@ -79,6 +141,7 @@ SR_HD void sub(Fe& r, const Fe& a, const Fe& b) {
         r.v[i] = (u32)c;
         c >>= 32;
     }
+#endif
 }
 
 // One CIOS round: t += a * bi; then t = (t + m p) / 2^32 with m = -t0.
@@ -107,8 +170,85 @@ SR_HD void mont_round(u32 (&t)[L + 2], const u32 (&a)[L], u32 bi) {
     t[L - 1] = (u32)c;
     t[L] = t[L + 1] + (u32)(c >> 32);
 }
+#if defined(__CUDA_ARCH__)
+// Device path: the same CIOS rounds written as carry chains of 32-bit multiply-adds.  Each round
+// adds a * b_i in two chains of four (lo, hi) pairs -- even limbs of a into the aligned pairs
+// (t0,t1)...(t6,t7), odd limbs into (t1,t2)...(t7,t8) -- which ptxas fuses into IMAD.WIDE.U32
+// with carry, then folds m * p with m = -t0 (p = 1 + 0x11 * 2^192 + 2^27 * 2^224).
+// Bound: a, b < p  =>  t < 2p < 2^253 between rounds and t + a b_i + m p < 2^286, so nine limbs
+// are enough and the chain carries into t8 can never overflow.
+SR_D void mont_round_ptx(u32 (&t)[L + 1], const u32 (&a)[L], u32 bi) {
+    asm volatile(
+        "mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
+        "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
+        "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+        "addc.u32        %8, %8, 0;\n\t"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+    asm volatile(
+        "mad.lo.cc.u32   %0, %8,  %12, %0;\n\t"
+        "madc.hi.cc.u32  %1, %8,  %12, %1;\n\t"
+        "madc.lo.cc.u32  %2, %9,  %12, %2;\n\t"
+        "madc.hi.cc.u32  %3, %9,  %12, %3;\n\t"
+        "madc.lo.cc.u32  %4, %10, %12, %4;\n\t"
+        "madc.hi.cc.u32  %5, %10, %12, %5;\n\t"
+        "madc.lo.cc.u32  %6, %11, %12, %6;\n\t"
+        "madc.hi.cc.u32  %7, %11, %12, %7;\n\t"
+        : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+        : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi));
+    // t += m p with m = -t0; afterwards t0 == 0 and the value is shifted down one limb
+    u32 m = 0u - t[0];
+    asm volatile(
+        "add.cc.u32      %0, %0, %9;\n\t"   // t0 + m = 2^32 or 0
+        "addc.cc.u32     %1, %1, 0;\n\t"
+        "addc.cc.u32     %2, %2, 0;\n\t"
+        "addc.cc.u32     %3, %3, 0;\n\t"
+        "addc.cc.u32     %4, %4, 0;\n\t"
+        "addc.cc.u32     %5, %5, 0;\n\t"
+        "madc.lo.cc.u32  %6, %9, 0x11, %6;\n\t"
+        "madc.hi.cc.u32  %7, %9, 0x11, %7;\n\t"
+        "addc.u32        %8, %8, 0;\n\t"
+        "mad.lo.cc.u32   %7, %9, 0x08000000, %7;\n\t"
+        "madc.hi.u32     %8, %9, 0x08000000, %8;\n\t"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
+        : "r"(m));
+#pragma unroll
+    for (int k = 0; k < L; k++) t[k] = t[k + 1];
+    t[L] = 0;
+}
+#endif
+
 // r = a * b * 2^-256 mod p (canonical output for canonical inputs)
 SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
+#if defined(__CUDA_ARCH__)
+    u32 t[L + 1];
+#pragma unroll
+    for (int i = 0; i < L + 1; i++) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) mont_round_ptx(t, a, b[i]);
+    // t < 2p: d = t - p, keep t if that borrowed
+    u32 d[L], br;
+    asm volatile(
+        "sub.cc.u32   %0, %9,  1;\n\t"
+        "subc.cc.u32  %1, %10, 0;\n\t"
+        "subc.cc.u32  %2, %11, 0;\n\t"
+        "subc.cc.u32  %3, %12, 0;\n\t"
+        "subc.cc.u32  %4, %13, 0;\n\t"
+        "subc.cc.u32  %5, %14, 0;\n\t"
+        "subc.cc.u32  %6, %15, 0x11;\n\t"
+        "subc.cc.u32  %7, %16, 0x08000000;\n\t"
+        "subc.u32     %8, 0, 0;\n\t"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7]), "=r"(br)
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]));
+#pragma unroll
+    for (int i = 0; i < L; i++) r.v[i] = br ? t[i] : d[i];
+    return;
+#else
     u32 t[L + 2];
 #pragma unroll
     for (int i = 0; i < L + 2; i++) t[i] = 0;
@@ -126,6 +266,7 @@ SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
     bool keep_t = br && (t[L] == 0);
 #pragma unroll
     for (int i = 0; i < L; i++) r.v[i] = keep_t ? t[i] : d[i];
+#endif
 }
 SR_HD void mont_mul(Fe& r, const Fe& a, const Fe& b) { mont_mul_limbs(r, a.v, b.v); }
 
