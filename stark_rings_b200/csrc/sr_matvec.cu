@@ -14,6 +14,7 @@
 #include "bb_ring.cuh"
 #include "gl_ring.cuh"
 #include "sp_ring.cuh"
+#include "sr_tma.cuh"
 
 namespace sr {
 
@@ -95,6 +96,346 @@ struct SPSlot {
     SR_D static void acc(Val& s, const Val& x) { Val t; sp::add(t, s, x); s = t; }
 };
 
+// ---- Goldilocks: lazy accumulation ---------------------------------------------------------------
+// sum_j a_j * x_j of 64 x 64 -> 128-bit products is kept UNREDUCED in a 160-bit accumulator held as two
+// interleaved carry-save halves (E: limbs 0..4 takes lo*lo and hi*hi, O: limbs 1..3 takes the two
+// cross products), so that every partial product is one IMAD.WIDE.U32 with carry and no modular
+// reduction happens inside the column loop.  One reduction per thread at the end.
+struct GLAcc {
+    u32 e0, e1, e2, e3, e4, o1, o2, o3;
+};
+SR_D void gl_acc_zero(GLAcc& A) { A.e0 = A.e1 = A.e2 = A.e3 = A.e4 = A.o1 = A.o2 = A.o3 = 0; }
+SR_D void gl_acc_mad(GLAcc& A, u64 a, u64 b) {
+    const u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
+    asm(
+        "mad.lo.cc.u32   %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32  %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32  %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32  %3, %6, %8, %3;\n\t"
+        "addc.u32        %4, %4, 0;\n\t"
+        : "+r"(A.e0), "+r"(A.e1), "+r"(A.e2), "+r"(A.e3), "+r"(A.e4)
+        : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+    asm(
+        "mad.lo.cc.u32   %0, %3, %6, %0;\n\t"
+        "madc.hi.cc.u32  %1, %3, %6, %1;\n\t"
+        "addc.u32        %2, %2, 0;\n\t"
+        "mad.lo.cc.u32   %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32  %1, %4, %5, %1;\n\t"
+        "addc.u32        %2, %2, 0;\n\t"
+        : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3)
+        : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+}
+// canonical residue of the accumulated value times 2^POST
+template <int POST>
+SR_D u64 gl_acc_reduce(const GLAcc& A) {
+    // merge: limbs l0..l5 of E + O * 2^32
+    u64 c = (u64)A.e1 + A.o1;
+    const u32 l0 = A.e0, l1 = (u32)c;
+    c = (c >> 32) + (u64)A.e2 + A.o2;
+    const u32 l2 = (u32)c;
+    c = (c >> 32) + (u64)A.e3 + A.o3;
+    const u32 l3 = (u32)c;
+    c = (c >> 32) + (u64)A.e4;
+    const u32 l4 = (u32)c, l5 = (u32)(c >> 32);
+    // 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32, 2^160 = 1 - 2^32 (mod p)
+    u64 r = gl::reduce128((u64)l0 | ((u64)l1 << 32), (u64)l2 | ((u64)l3 << 32));
+    r = gl::sub(r, (u64)l4 << 32);
+    r = gl::add(r, (u64)l5);
+    r = gl::sub(r, (u64)l5 << 32);
+    return POST ? gl::mul_pow2<POST>(r) : r;
+}
+
+#ifndef SR_GLMV_MINB
+#define SR_GLMV_MINB 2
+#endif
+#ifndef SR_GLMV_RB
+#define SR_GLMV_RB 4
+#endif
+constexpr int GLMV_T = 128;
+// Rows [row0, row0 + RB) of the product; same work split and partial layout as matvec_partial_kernel.
+template <int RB>
+__global__ void __launch_bounds__(GLMV_T, SR_GLMV_MINB)
+gl_matvec_lazy_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
+                      const u64* __restrict__ v, u64* __restrict__ partial) {
+    typedef GLSlot S;
+    __shared__ S::Val red[GLMV_T];
+    GLAcc acc[RB][3];
+#pragma unroll
+    for (int r = 0; r < RB; r++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) gl_acc_zero(acc[r][k]);
+    const u64* rp[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) rp[r] = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
+
+    const size_t total = ncols * S::SLOTS;
+    const size_t stride = (size_t)gridDim.x * GLMV_T;
+    for (size_t g = (size_t)blockIdx.x * GLMV_T + threadIdx.x; g < total; g += stride) {
+        u64 a[RB][3];
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            a[r][0] = __ldcs(rp[r] + g * 3);
+            a[r][1] = __ldcs(rp[r] + g * 3 + 1);
+            a[r][2] = __ldcs(rp[r] + g * 3 + 2);
+        }
+        const u64 x0 = v[g * 3], x1 = v[g * 3 + 1], x2 = v[g * 3 + 2];
+        const u64 xr1 = gl::mul_pow2<gl::root_exp(1)>(x1), xr2 = gl::mul_pow2<gl::root_exp(1)>(x2);  // u^3 = r
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            gl_acc_mad(acc[r][0], a[r][0], x0);
+            gl_acc_mad(acc[r][0], a[r][1], xr2);
+            gl_acc_mad(acc[r][0], a[r][2], xr1);
+            gl_acc_mad(acc[r][1], a[r][0], x1);
+            gl_acc_mad(acc[r][1], a[r][1], x0);
+            gl_acc_mad(acc[r][1], a[r][2], xr2);
+            gl_acc_mad(acc[r][2], a[r][0], x2);
+            gl_acc_mad(acc[r][2], a[r][1], x1);
+            gl_acc_mad(acc[r][2], a[r][2], x0);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (row0 + r >= nrows) break;
+        S::Val mine;  // Montgomery layout: the product of two raw limbs carries an extra 2^-64 = 2^128
+#pragma unroll
+        for (int k = 0; k < 3; k++) mine.c[k] = gl_acc_reduce<128>(acc[r][k]);
+        red[threadIdx.x] = mine;
+        __syncthreads();
+        if (threadIdx.x < S::SLOTS) {
+            S::Val s = red[threadIdx.x];
+            for (int k = threadIdx.x + S::SLOTS; k < GLMV_T; k += S::SLOTS) S::acc(s, red[k]);
+            S::store(partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, s);
+        }
+        __syncthreads();
+    }
+}
+
+// TMA-pipelined flavour: the CTA streams chunks of GLTMA_T consecutive slots (3072 B) of v and of RB
+// matrix rows through an NS-deep ring of shared-memory stages filled by 1-D bulk copies
+// (cp.async.bulk + mbarrier complete_tx), so HBM requests are whole 128-byte lines issued far ahead of
+// use and the per-thread 24-byte slot reads hit shared memory (stride 6 words: conflict-free LDS.64).
+constexpr int GLTMA_T = 128, GLTMA_NS = 4;
+template <int RB>
+__global__ void __launch_bounds__(GLTMA_T, 2)
+gl_matvec_tma_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
+                     const u64* __restrict__ v, u64* __restrict__ partial) {
+    typedef GLSlot S;
+    constexpr int CS = GLTMA_T;                  // slots per chunk
+    constexpr uint32_t ROWB = CS * 24;           // bytes per row per stage
+    extern __shared__ __align__(128) unsigned char smem[];
+    u64* stage = reinterpret_cast<u64*>(smem);   // [NS][RB + 1][CS * 3]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)GLTMA_NS * (RB + 1) * ROWB);
+    __shared__ S::Val red[GLTMA_T];
+
+    const u64* rp[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) rp[r] = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
+    const size_t total = ncols * S::SLOTS;
+    const size_t nchunks = (total + CS - 1) / CS;
+    const size_t my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GLTMA_NS; s++) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](size_t it) {  // thread 0 only
+        const int s = (int)(it % GLTMA_NS);
+        const size_t chunk = blockIdx.x + it * gridDim.x;
+        const size_t slot0 = chunk * CS;
+        const uint32_t bytes = (uint32_t)(((total - slot0 < (size_t)CS) ? (total - slot0) : (size_t)CS) * 24);
+        mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
+        u64* dst = stage + (size_t)s * (RB + 1) * CS * 3;
+        tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
+#pragma unroll
+        for (int r = 0; r < RB; r++) tma_load_1d(dst + (size_t)(r + 1) * CS * 3, rp[r] + slot0 * 3, bytes, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (size_t it = 0; it < (size_t)GLTMA_NS && it < my_chunks; it++) issue(it);
+
+    GLAcc acc[RB][3];
+#pragma unroll
+    for (int r = 0; r < RB; r++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) gl_acc_zero(acc[r][k]);
+
+    for (size_t it = 0; it < my_chunks; it++) {
+        const int s = (int)(it % GLTMA_NS);
+        mbar_wait(&full[s], (uint32_t)((it / GLTMA_NS) & 1));
+        const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
+        const bool live = slot0 + threadIdx.x < total;
+        const u64* base = stage + (size_t)s * (RB + 1) * CS * 3 + threadIdx.x * 3;
+        u64 x0 = 0, x1 = 0, x2 = 0, a[RB][3];
+        if (live) { x0 = base[0]; x1 = base[1]; x2 = base[2]; }
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const u64* q = base + (size_t)(r + 1) * CS * 3;
+            a[r][0] = live ? q[0] : 0; a[r][1] = live ? q[1] : 0; a[r][2] = live ? q[2] : 0;
+        }
+        __syncthreads();  // every thread has read stage s: it can be refilled
+        if (threadIdx.x == 0 && it + GLTMA_NS < my_chunks) issue(it + GLTMA_NS);
+        const u64 xr1 = gl::mul_pow2<gl::root_exp(1)>(x1), xr2 = gl::mul_pow2<gl::root_exp(1)>(x2);
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            gl_acc_mad(acc[r][0], a[r][0], x0);
+            gl_acc_mad(acc[r][0], a[r][1], xr2);
+            gl_acc_mad(acc[r][0], a[r][2], xr1);
+            gl_acc_mad(acc[r][1], a[r][0], x1);
+            gl_acc_mad(acc[r][1], a[r][1], x0);
+            gl_acc_mad(acc[r][1], a[r][2], xr2);
+            gl_acc_mad(acc[r][2], a[r][0], x2);
+            gl_acc_mad(acc[r][2], a[r][1], x1);
+            gl_acc_mad(acc[r][2], a[r][2], x0);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (row0 + r >= nrows) break;
+        S::Val mine;
+#pragma unroll
+        for (int k = 0; k < 3; k++) mine.c[k] = gl_acc_reduce<128>(acc[r][k]);
+        red[threadIdx.x] = mine;
+        __syncthreads();
+        if (threadIdx.x < S::SLOTS) {
+            S::Val sacc = red[threadIdx.x];
+            for (int k = threadIdx.x + S::SLOTS; k < GLTMA_T; k += S::SLOTS) S::acc(sacc, red[k]);
+            S::store(partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, sacc);
+        }
+        __syncthreads();
+    }
+}
+
+template <int RB>
+static cudaError_t gl_tma_launch_rb(int grid, const u64* const* d_rows, size_t nrows, size_t row0, size_t ncols,
+                                    const u64* v, u64* parts, cudaStream_t st) {
+    auto kern = gl_matvec_tma_kernel<RB>;
+    const size_t smem = (size_t)GLTMA_NS * (RB + 1) * GLTMA_T * 24 + GLTMA_NS * sizeof(uint64_t);
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, GLTMA_T, smem, st>>>(d_rows, nrows, row0, ncols, v, parts);
+    return cudaGetLastError();
+}
+
+// Three threads per slot: the nine products of a slot product fall on five diagonals
+//   d0 = a0 x0, d1 = a0 x1 + a1 x0, d2 = a0 x2 + a1 x1 + a2 x0, d3 = a1 x2 + a2 x1, d4 = a2 x2,
+//   c0 = d0 + r d3, c1 = d1 + r d4, c2 = d2   (u^3 = r = 2^40),
+// and are split 3 + 3 + 3 over the threads (part 0: d0 | d3, part 1: d4 | d1, part 2: a0 x2 | a1 x1 + a2 x0),
+// each thread keeping two lazy accumulators per matrix row.  No multiplication by r and no reduction
+// inside the column loop; operand indices are per-lane constants, so all lanes run one instruction
+// stream.  ~100 registers -> 18 warps per SM instead of 8.
+#ifndef SR_GL3_MINB
+#define SR_GL3_MINB 2
+#endif
+constexpr int GL3_SLOTS = 64, GL3_T = 3 * GL3_SLOTS, GL3_NS = 4;
+template <int RB>
+__global__ void __launch_bounds__(GL3_T, SR_GL3_MINB)
+gl_matvec_tma3_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
+                      const u64* __restrict__ v, u64* __restrict__ partial) {
+    typedef GLSlot S;
+    constexpr int CS = GL3_SLOTS;
+    constexpr uint32_t ROWB = CS * 24;
+    extern __shared__ __align__(128) unsigned char smem[];
+    u64* stage = reinterpret_cast<u64*>(smem);   // [NS][RB + 1][CS * 3]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)GL3_NS * (RB + 1) * ROWB);
+    __shared__ u64 red[GL3_SLOTS][3];
+
+    const int slot = threadIdx.x / 3, part = threadIdx.x - 3 * slot;
+    // operand indices: accA += a[ia] x[ja];  accB += a[ib1] x[jb1] + a[ib2] x[jb2]
+    const int ia = (part == 1) ? 2 : 0, ja = (part == 0) ? 0 : 2;
+    const int ib1 = (part == 1) ? 0 : 1, jb1 = (part == 0) ? 2 : 1;
+    const int ib2 = (part == 1) ? 1 : 2, jb2 = (part == 0) ? 1 : 0;
+
+    const u64* rp[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) rp[r] = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
+    const size_t total = ncols * S::SLOTS;
+    const size_t nchunks = (total + CS - 1) / CS;
+    const size_t my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GL3_NS; s++) mbar_init(&full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](size_t it) {
+        const int s = (int)(it % GL3_NS);
+        const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
+        const uint32_t bytes = (uint32_t)(((total - slot0 < (size_t)CS) ? (total - slot0) : (size_t)CS) * 24);
+        mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
+        u64* dst = stage + (size_t)s * (RB + 1) * CS * 3;
+        tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
+#pragma unroll
+        for (int r = 0; r < RB; r++) tma_load_1d(dst + (size_t)(r + 1) * CS * 3, rp[r] + slot0 * 3, bytes, &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (size_t it = 0; it < (size_t)GL3_NS && it < my_chunks; it++) issue(it);
+
+    GLAcc accA[RB], accB[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) { gl_acc_zero(accA[r]); gl_acc_zero(accB[r]); }
+
+    for (size_t it = 0; it < my_chunks; it++) {
+        const int s = (int)(it % GL3_NS);
+        mbar_wait(&full[s], (uint32_t)((it / GL3_NS) & 1));
+        const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
+        const bool live = slot0 + slot < total;
+        const u64* base = stage + (size_t)s * (RB + 1) * CS * 3 + slot * 3;
+        u64 xa = 0, xb1 = 0, xb2 = 0, aa[RB], ab1[RB], ab2[RB];
+        if (live) { xa = base[ja]; xb1 = base[jb1]; xb2 = base[jb2]; }
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const u64* q = base + (size_t)(r + 1) * CS * 3;
+            aa[r] = live ? q[ia] : 0; ab1[r] = live ? q[ib1] : 0; ab2[r] = live ? q[ib2] : 0;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && it + GL3_NS < my_chunks) issue(it + GL3_NS);
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            gl_acc_mad(accA[r], aa[r], xa);
+            gl_acc_mad(accB[r], ab1[r], xb1);
+            gl_acc_mad(accB[r], ab2[r], xb2);
+        }
+    }
+    // thread -> one coefficient of the slot: part 0: c0 = A + r B, part 1: c1 = B + r A, part 2: c2 = A + B
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (row0 + r >= nrows) break;
+        const u64 ra = gl_acc_reduce<0>(accA[r]), rb = gl_acc_reduce<0>(accB[r]);
+        u64 c;
+        if (part == 0) c = gl::add(ra, gl::mul_pow2<gl::root_exp(1)>(rb));
+        else if (part == 1) c = gl::add(rb, gl::mul_pow2<gl::root_exp(1)>(ra));
+        else c = gl::add(ra, rb);
+        red[slot][part] = gl::mul_pow2<128>(c);  // Montgomery layout: extra 2^-64 = 2^128
+        __syncthreads();
+        if (threadIdx.x < S::SLOTS * 3) {  // 24 threads: (slot index s8, coefficient k)
+            const int s8 = threadIdx.x / 3, k = threadIdx.x - 3 * s8;
+            u64 acc = 0;
+            for (int q = s8; q < GL3_SLOTS; q += S::SLOTS) acc = gl::add(acc, red[q][k]);
+            partial[((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + s8 * 3 + k] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+template <int RB>
+static cudaError_t gl_tma3_launch_rb(int grid, const u64* const* d_rows, size_t nrows, size_t row0, size_t ncols,
+                                     const u64* v, u64* parts, cudaStream_t st) {
+    auto kern = gl_matvec_tma3_kernel<RB>;
+    const size_t smem = (size_t)GL3_NS * (RB + 1) * GL3_SLOTS * 24 + GL3_NS * sizeof(uint64_t);
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    kern<<<grid, GL3_T, smem, st>>>(d_rows, nrows, row0, ncols, v, parts);
+    return cudaGetLastError();
+}
+
 constexpr int MV_T = 256;  // threads per CTA (multiple of every SLOTS)
 
 // partial[(blockIdx * nrows + row) * ELEM + slot*SLOT_U64 ...] = CTA-local sum for rows [row0, row0+RB)
@@ -151,6 +492,66 @@ __global__ void sum_partials_kernel(const u64* __restrict__ parts, size_t nparts
 
 static int mv_grid(int sms) { return sms * 4; }
 
+static cudaError_t gl_matvec_launch(const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v, u64* out,
+                                    void* scratch, cudaStream_t st, int sms, int* launches) {
+    typedef GLSlot S;
+    *launches = 0;
+    if (nrows == 0) return cudaSuccess;
+    if (ncols == 0) return cudaMemsetAsync(out, 0, nrows * S::ELEM_U64 * 8, st);
+    size_t total = ncols * S::SLOTS;
+    int grid = mv_grid(sms);  // scratch is sized for mv_grid(sms) partials
+    size_t need = (total + GLMV_T - 1) / GLMV_T;
+    if ((size_t)grid > need) grid = (int)need;
+    u64* parts = reinterpret_cast<u64*>(scratch);
+    size_t row0 = 0;
+#if defined(SR_GLMV_TMA3)
+    {
+        int g2 = sms * SR_GL3_MINB;
+        const size_t nchunks = (total + GL3_SLOTS - 1) / GL3_SLOTS;
+        if ((size_t)g2 > nchunks) g2 = (int)nchunks;
+        while (row0 < nrows) {
+            const size_t left = nrows - row0;
+            cudaError_t e;
+            if (left >= 4) { e = gl_tma3_launch_rb<4>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 4; }
+            else if (left >= 2) { e = gl_tma3_launch_rb<2>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 2; }
+            else { e = gl_tma3_launch_rb<1>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 1; }
+            if (e != cudaSuccess) return e;
+            (*launches)++;
+        }
+        grid = g2;
+    }
+#elif !defined(SR_GLMV_NO_TMA)
+    {
+        int g2 = sms * 2;  // two resident CTAs per SM
+        const size_t nchunks = (total + GLTMA_T - 1) / GLTMA_T;
+        if ((size_t)g2 > nchunks) g2 = (int)nchunks;
+        while (row0 < nrows) {
+            const size_t left = nrows - row0;
+            cudaError_t e;
+            if (left >= 4) { e = gl_tma_launch_rb<4>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 4; }
+            else if (left >= 2) { e = gl_tma_launch_rb<2>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 2; }
+            else { e = gl_tma_launch_rb<1>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 1; }
+            if (e != cudaSuccess) return e;
+            (*launches)++;
+        }
+        grid = g2;
+    }
+#endif
+    while (row0 < nrows) {
+        const size_t left = nrows - row0;
+        if (left >= 4 && SR_GLMV_RB >= 4) { gl_matvec_lazy_kernel<4><<<grid, GLMV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, parts); row0 += 4; }
+        else if (left >= 2) { gl_matvec_lazy_kernel<2><<<grid, GLMV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, parts); row0 += 2; }
+        else { gl_matvec_lazy_kernel<1><<<grid, GLMV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, parts); row0 += 1; }
+        (*launches)++;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t n = nrows * S::SLOTS;
+    sum_partials_kernel<S><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(parts, (size_t)grid, nrows, out);
+    (*launches)++;
+    return cudaGetLastError();
+}
+
 size_t matvec_scratch_bytes(int ring, size_t nrows, int sms) {
     const size_t w = ring == RING_GL ? 24 : ring == RING_BB ? 72 : 64;
     return (size_t)mv_grid(sms) * nrows * w * 8 + 16;
@@ -183,7 +584,7 @@ static cudaError_t matvec_launch_t(const u64* const* d_rows, size_t nrows, size_
 cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v, u64* out,
                           void* scratch, cudaStream_t st, int sms, int* launches) {
     switch (ring) {
-    case RING_GL: return matvec_launch_t<GLSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches);
+    case RING_GL: return gl_matvec_launch(d_rows, nrows, ncols, v, out, scratch, st, sms, launches);
     case RING_BB: return matvec_launch_t<BBSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches);
     case RING_SP: return matvec_launch_t<SPSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches);
     }
