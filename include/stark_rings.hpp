@@ -1,0 +1,170 @@
+// stark_rings.hpp -- header-only C++ mirror of the reference's operator surface for the hot path,
+// over the C ABI in stark_rings_cuda.h.  (The reference is Rust; no Rust toolchain exists in the
+// build image, so the compiled-language host side is C++ -- see INTEGRATION.md for the Rust shim.)
+//
+//   reference (crates/ring/src/cyclotomic_ring/...)              here
+//   ring_config.rs:11-35  CyclotomicConfig::{crt,icrt}_in_place    RingConfig<...>::crt_in_place / icrt_in_place
+//   coeff_form.rs:31-33   CyclotomicPolyRingGeneral  (RqPoly)      RqPoly<C>   (a batch of n >= 1 elements)
+//   ntt_form.rs:25-27     CyclotomicPolyRingNTTGeneral (RqNTT)     RqNTT<C>
+//   crt.rs:6-50           CRT / ICRT, elementwise_crt / _icrt      RqPoly::crt(), RqNTT::icrt(), CRT<C>, ICRT<C>
+//   ntt_form.rs:159-189   Mul / MulUnchecked                       RqNTT::operator*=, mul_unchecked
+//   coeff_form.rs:250-258 Mul (poly_mul + reduce)                  RqPoly::operator*  (fused kernel)
+//   linear_algebra/src/matrix.rs:168-183  checked/try_mul_vec      Matrix<C>::checked_mul_vec / try_mul_vec
+//   linear_algebra/src/error.rs:3-8       AlgebraError             DifferentLengths
+// Buffers are raw ark-ff limbs (little-endian u64, Montgomery form) in host memory; every call goes
+// to libstarkrings_cuda.so -- there is no CPU implementation behind this header.
+#pragma once
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "stark_rings_cuda.h"
+
+namespace stark_rings {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+// wrong slice length: the reference panics (assert_eq!(coefficients.len(), D))
+struct LengthPanic : std::logic_error {
+    using std::logic_error::logic_error;
+};
+// AlgebraError::DifferentLengths(usize, usize)
+struct DifferentLengths : std::runtime_error {
+    size_t lhs, rhs;
+    DifferentLengths(size_t a, size_t b)
+        : std::runtime_error("Unexpected different lengths: " + std::to_string(a) + " and " + std::to_string(b)),
+          lhs(a), rhs(b) {}
+};
+
+class Context {
+public:
+    explicit Context(int device = 0) {
+        if (sr_init(device, &h_) != SR_OK) throw Error("sr_init failed: no usable sm_100 GPU (no CPU fallback)");
+    }
+    ~Context() { if (h_) sr_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    sr_ctx* get() const { return h_; }
+    void check(int rc, const char* what) const {
+        if (rc == SR_OK) return;
+        std::string msg = std::string(what) + ": " + sr_last_error(h_);
+        if (rc == SR_ERR_BAD_LENGTH) throw LengthPanic(msg);
+        throw Error(msg);
+    }
+    static Context& global() { static Context c(0); return c; }
+private:
+    sr_ctx* h_ = nullptr;
+};
+
+// CyclotomicConfig<N>: RING = sr_ring id, D = ring dimension, N = u64 limbs per field element
+template <int RING, size_t D_, size_t N_, size_t EXT>
+struct RingConfig {
+    static constexpr int ring = RING;
+    static constexpr size_t D = D_, N = N_, LIMBS = D_ * N_, CRT_FIELD_EXTENSION_DEGREE = EXT;
+    // one element (D field elements), in place; any other length panics like the reference
+    static void crt_in_place(uint64_t* coefficients, size_t n_limbs) {
+        if (n_limbs != LIMBS) throw LengthPanic("crt_in_place: wrong slice length");
+        Context::global().check(sr_crt_batch(Context::global().get(), RING, coefficients, n_limbs, SR_HOST), "crt");
+    }
+    static void icrt_in_place(uint64_t* evaluations, size_t n_limbs) {
+        if (n_limbs != LIMBS) throw LengthPanic("icrt_in_place: wrong slice length");
+        Context::global().check(sr_icrt_batch(Context::global().get(), RING, evaluations, n_limbs, SR_HOST), "icrt");
+    }
+};
+using GoldilocksRingConfig = RingConfig<SR_GOLDILOCKS, 24, 1, 3>;
+using BabyBearRingConfig = RingConfig<SR_BABYBEAR, 72, 1, 9>;
+using StarkRingConfig = RingConfig<SR_STARK, 16, 4, 1>;
+
+template <class C> struct RqNTT;
+
+// A batch of coefficient-form elements over one flat limb buffer (len() == 1: a single element).
+template <class C>
+struct RqPoly {
+    std::vector<uint64_t> limbs;
+    RqPoly() = default;
+    explicit RqPoly(std::vector<uint64_t> raw) : limbs(std::move(raw)) {
+        if (limbs.size() % C::LIMBS) throw LengthPanic("buffer is not a whole number of ring elements");
+    }
+    size_t len() const { return limbs.size() / C::LIMBS; }
+    static constexpr size_t dimension() { return C::D; }
+    RqNTT<C> crt() &&;                       // CRT::crt / elementwise_crt: consumes self, same allocation
+    RqPoly operator*(const RqPoly& rhs) const {  // coeff_form.rs Mul == icrt(crt(a) * crt(b)), one kernel
+        if (rhs.limbs.size() != limbs.size()) throw LengthPanic("operands differ in length");
+        RqPoly out;
+        out.limbs.resize(limbs.size());
+        auto& c = Context::global();
+        c.check(sr_ring_mul_batch(c.get(), C::ring, limbs.data(), rhs.limbs.data(), out.limbs.data(), limbs.size(),
+                                  SR_HOST), "ring_mul");
+        return out;
+    }
+    bool operator==(const RqPoly& o) const { return limbs == o.limbs; }
+};
+
+template <class C>
+struct RqNTT {
+    std::vector<uint64_t> limbs;
+    RqNTT() = default;
+    explicit RqNTT(std::vector<uint64_t> raw) : limbs(std::move(raw)) {
+        if (limbs.size() % C::LIMBS) throw LengthPanic("buffer is not a whole number of ring elements");
+    }
+    size_t len() const { return limbs.size() / C::LIMBS; }
+    RqPoly<C> icrt() && {                    // ICRT::icrt / elementwise_icrt
+        auto& c = Context::global();
+        c.check(sr_icrt_batch(c.get(), C::ring, limbs.data(), limbs.size(), SR_HOST), "icrt");
+        return RqPoly<C>(std::move(limbs));
+    }
+    RqNTT& operator*=(const RqNTT& rhs) {    // ntt_form.rs:159-175, slot-wise
+        if (rhs.limbs.size() != limbs.size()) throw LengthPanic("operands differ in length");
+        auto& c = Context::global();
+        c.check(sr_ntt_mul_batch(c.get(), C::ring, limbs.data(), rhs.limbs.data(), limbs.size(), SR_HOST), "ntt_mul");
+        return *this;
+    }
+    RqNTT operator*(const RqNTT& rhs) const { RqNTT t(*this); t *= rhs; return t; }
+    RqNTT mul_unchecked(const RqNTT& rhs) const { return *this * rhs; }  // ntt_form.rs:177-189
+    bool operator==(const RqNTT& o) const { return limbs == o.limbs; }
+};
+
+template <class C>
+RqNTT<C> RqPoly<C>::crt() && {
+    auto& c = Context::global();
+    c.check(sr_crt_batch(c.get(), C::ring, limbs.data(), limbs.size(), SR_HOST), "crt");
+    return RqNTT<C>(std::move(limbs));
+}
+
+template <class C> struct CRT { static RqNTT<C> elementwise_crt(RqPoly<C>&& v) { return std::move(v).crt(); } };
+template <class C> struct ICRT { static RqPoly<C> elementwise_icrt(RqNTT<C>&& v) { return std::move(v).icrt(); } };
+
+// Matrix { nrows, ncols, vals: Vec<Vec<R>> } with R = RqNTT (each row its own allocation)
+template <class C>
+struct Matrix {
+    size_t nrows = 0, ncols = 0;
+    std::vector<RqNTT<C>> vals;
+    explicit Matrix(std::vector<RqNTT<C>> rows) : vals(std::move(rows)) {
+        nrows = vals.size();
+        ncols = nrows ? vals[0].len() : 0;
+        for (auto& r : vals) if (r.len() != ncols) throw std::invalid_argument("ragged matrix");
+    }
+    std::optional<RqNTT<C>> checked_mul_vec(const RqNTT<C>& v) const {  // None when ncols != v.len()
+        std::vector<const uint64_t*> ptrs(nrows);
+        for (size_t i = 0; i < nrows; i++) ptrs[i] = vals[i].limbs.data();
+        RqNTT<C> out;
+        out.limbs.resize(nrows * C::LIMBS);
+        auto& c = Context::global();
+        int rc = sr_matvec(c.get(), C::ring, ptrs.data(), nrows, ncols, v.limbs.data(), v.limbs.size(),
+                           out.limbs.data(), SR_HOST);
+        if (rc == SR_ERR_BAD_LENGTH) return std::nullopt;
+        c.check(rc, "matvec");
+        return out;
+    }
+    RqNTT<C> try_mul_vec(const RqNTT<C>& v) const {  // Err(DifferentLengths(ncols, v.len()))
+        auto r = checked_mul_vec(v);
+        if (!r) throw DifferentLengths(ncols, v.len());
+        return *r;
+    }
+};
+
+}  // namespace stark_rings

@@ -478,16 +478,32 @@ matvec_partial_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t 
     }
 }
 
-// out[row] = sum_k parts[k * nrows + row]  (k < nparts), one thread per (row, slot)
+// out[row] = sum_k parts[k * nrows + row]  (k < nparts).  One warp per (row, slot): the lanes stride over
+// the partials, then a shared-memory tree adds the 32 lane sums in a fixed order (deterministic).
 template <class S>
-__global__ void sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t nrows, u64* __restrict__ out) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nrows * S::SLOTS) return;
-    const size_t row = idx / S::SLOTS, slot = idx % S::SLOTS;
+__global__ void __launch_bounds__(128)
+sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t nrows, u64* __restrict__ out) {
+    __shared__ typename S::Val red[128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t idx = (size_t)blockIdx.x * 4 + warp;  // (row, slot)
+    const bool live = idx < nrows * S::SLOTS;
+    const size_t row = live ? idx / S::SLOTS : 0, slot = live ? idx % S::SLOTS : 0;
     typename S::Val s = S::zero();
-    for (size_t k = 0; k < nparts; k++)
-        S::acc(s, S::load_cached(parts + (k * nrows + row) * S::ELEM_U64 + slot * S::SLOT_U64));
-    S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, s);
+    if (live)
+        for (size_t k = lane; k < nparts; k += 32)
+            S::acc(s, S::load_cached(parts + (k * nrows + row) * S::ELEM_U64 + slot * S::SLOT_U64));
+    red[threadIdx.x] = s;
+    __syncwarp();
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        if (lane < w) {
+            typename S::Val t = red[threadIdx.x];
+            S::acc(t, red[threadIdx.x + w]);
+            red[threadIdx.x] = t;
+        }
+        __syncwarp();
+    }
+    if (live && lane == 0) S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, red[threadIdx.x]);
 }
 
 static int mv_grid(int sms) { return sms * 4; }
@@ -547,7 +563,7 @@ static cudaError_t gl_matvec_launch(const u64* const* d_rows, size_t nrows, size
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(parts, (size_t)grid, nrows, out);
+    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(parts, (size_t)grid, nrows, out);
     (*launches)++;
     return cudaGetLastError();
 }
@@ -576,7 +592,7 @@ static cudaError_t matvec_launch_t(const u64* const* d_rows, size_t nrows, size_
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(parts, (size_t)grid, nrows, out);
+    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(parts, (size_t)grid, nrows, out);
     (*launches)++;
     return cudaGetLastError();
 }
@@ -594,7 +610,7 @@ cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size
 template <class S>
 static cudaError_t modsum_t(const u64* g, size_t nranks, size_t nrows, u64* out, cudaStream_t st) {
     const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g, nranks, nrows, out);
+    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(g, nranks, nrows, out);
     return cudaGetLastError();
 }
 cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t nrows, u64* out, cudaStream_t st) {
