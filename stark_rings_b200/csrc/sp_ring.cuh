@@ -223,14 +223,102 @@ SR_D void mont_round_ptx(u32 (&t)[L + 1], const u32 (&a)[L], u32 bi) {
 }
 #endif
 
+#if defined(__CUDA_ARCH__)
+// Even/odd carry-save form of the same CIOS round (no register moves): the running value is
+//   T = X + Y * 2^32 + z,   X = limbs 0..8 in even-aligned pairs (0,1)(2,3)(4,5)(6,7),
+//                           Y = limbs 1..8 in odd-aligned pairs  (1,2)(3,4)(5,6)(7,8)   (Y[j] = limb j+1),
+//                           z = a pending addend at limb 0 (zlo + 2^32 zhi, zhi <= 1).
+// a_even * b_i goes into X, a_odd * b_i into Y, each as one chain of four IMAD.WIDE with carry.  With
+// m = -(X0 + zlo), m * p adds m at limb 0 (cancelling it, carry k2), 0x11 m at the X pair (6,7) and
+// 2^27 m at the Y pair (7,8).  Dividing by 2^32 then swaps the roles: new X = old Y, new Y = old X >> 64,
+// and old X1 plus the limb-0 carries becomes the new pending addend.
+SR_D void mont_round_eo(u32 (&X)[L + 1], u32 (&Y)[L + 1], u32& zlo, u32& zhi, const u32 (&a)[L], u32 bi) {
+    // One carry-flag-linked instruction sequence per round (every chain starts with the carry-out,
+    // always 0, of the previous one) so that ptxas keeps a single live carry per multiplication.
+    u32 nzlo, nzhi;
+    asm volatile(
+        "{\n\t"
+        ".reg .u32 t0, tmp, m, k;\n\t"
+        "mad.lo.cc.u32   %0, %21, %29, %0;\n\t"
+        "madc.hi.cc.u32  %1, %21, %29, %1;\n\t"
+        "madc.lo.cc.u32  %2, %23, %29, %2;\n\t"
+        "madc.hi.cc.u32  %3, %23, %29, %3;\n\t"
+        "madc.lo.cc.u32  %4, %25, %29, %4;\n\t"
+        "madc.hi.cc.u32  %5, %25, %29, %5;\n\t"
+        "madc.lo.cc.u32  %6, %27, %29, %6;\n\t"
+        "madc.hi.cc.u32  %7, %27, %29, %7;\n\t"
+        "addc.cc.u32     %8, %8, 0;\n\t"
+        "madc.lo.cc.u32  %9,  %22, %29, %9;\n\t"
+        "madc.hi.cc.u32  %10, %22, %29, %10;\n\t"
+        "madc.lo.cc.u32  %11, %24, %29, %11;\n\t"
+        "madc.hi.cc.u32  %12, %24, %29, %12;\n\t"
+        "madc.lo.cc.u32  %13, %26, %29, %13;\n\t"
+        "madc.hi.cc.u32  %14, %26, %29, %14;\n\t"
+        "madc.lo.cc.u32  %15, %28, %29, %15;\n\t"
+        "madc.hi.cc.u32  %16, %28, %29, %16;\n\t"
+        "addc.cc.u32     t0, %0, %17;\n\t"      // limb 0: X0 + zlo
+        "addc.u32        k, %18, 0;\n\t"        // k = zhi + carry
+        "sub.u32         m, 0, t0;\n\t"         // m = -t0
+        "add.cc.u32      tmp, t0, m;\n\t"       // carry = [t0 != 0]
+        "addc.u32        k, k, 0;\n\t"
+        "add.cc.u32      %19, %1, k;\n\t"       // new pending addend: X1 + k
+        "addc.cc.u32     %20, 0, 0;\n\t"
+        "madc.lo.cc.u32  %6, m, 0x11, %6;\n\t"  // + 0x11 m at limbs (6,7)
+        "madc.hi.cc.u32  %7, m, 0x11, %7;\n\t"
+        "addc.cc.u32     %8, %8, 0;\n\t"
+        "madc.lo.cc.u32  %15, m, 0x08000000, %15;\n\t"  // + 2^27 m at limbs (7,8) = Y[6], Y[7]
+        "madc.hi.u32     %16, m, 0x08000000, %16;\n\t"
+        "}"
+        : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]), "+r"(X[8]),
+          "+r"(Y[0]), "+r"(Y[1]), "+r"(Y[2]), "+r"(Y[3]), "+r"(Y[4]), "+r"(Y[5]), "+r"(Y[6]), "+r"(Y[7]),
+          "+r"(zlo), "+r"(zhi), "=&r"(nzlo), "=&r"(nzhi)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(bi));
+    zlo = nzlo;
+    zhi = nzhi;
+    // divide by 2^32: new X = old Y (limbs 1..8 -> 0..7), new Y = old X limbs 2..8 (-> 1..7)
+    u32 nX[L + 1], nY[L + 1];
+#pragma unroll
+    for (int j = 0; j < L; j++) nX[j] = Y[j];
+    nX[L] = 0;
+#pragma unroll
+    for (int j = 0; j < L - 1; j++) nY[j] = X[j + 2];
+    nY[L - 1] = 0;
+    nY[L] = 0;
+#pragma unroll
+    for (int j = 0; j <= L; j++) {
+        X[j] = nX[j];
+        Y[j] = nY[j];
+    }
+}
+#endif
+
 // r = a * b * 2^-256 mod p (canonical output for canonical inputs)
 SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(SR_SP_MONT_EO)  // experimental: ptxas spills carry predicates (see profiles/r01_tuning.md)
+    u32 X[L + 1], Y[L + 1], zlo = 0, zhi = 0, t[L + 1];
+#pragma unroll
+    for (int i = 0; i < L + 1; i++) X[i] = Y[i] = 0;
+#pragma unroll
+    for (int i = 0; i < L; i++) mont_round_eo(X, Y, zlo, zhi, a, b[i]);
+    {   // merge T = X + Y * 2^32 + z
+        u64 c = (u64)X[0] + zlo;
+        t[0] = (u32)c;
+        c = (c >> 32) + (u64)X[1] + Y[0] + zhi;
+        t[1] = (u32)c;
+#pragma unroll
+        for (int j = 2; j <= L; j++) {
+            c = (c >> 32) + (u64)X[j] + Y[j - 1];
+            t[j] = (u32)c;
+        }
+    }
+#elif defined(__CUDA_ARCH__)
     u32 t[L + 1];
 #pragma unroll
     for (int i = 0; i < L + 1; i++) t[i] = 0;
 #pragma unroll
     for (int i = 0; i < L; i++) mont_round_ptx(t, a, b[i]);
+#endif
+#if defined(__CUDA_ARCH__)
     // t < 2p: d = t - p, keep t if that borrowed
     u32 d[L], br;
     asm volatile(
