@@ -7,6 +7,7 @@
 #include "bb_half.cuh"
 #include "bb_ring.cuh"
 #include "gl_ring.cuh"
+#include "sp_half.cuh"
 #include "sp_ring.cuh"
 
 using namespace sr;
@@ -84,6 +85,42 @@ void hc_sp_ring_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
     sp::crt(x); sp::crt(y);
     for (int i = 0; i < 16; i++) sp::mont_mul(y[i], y[i], x[i]);
     sp::icrt(y); memcpy(out, y, 512);
+}
+
+
+// two-threads-per-element formulation (sp_half.cuh), both halves in sequence
+static void sp_half_crt_host(sp::Fe (&pos)[2][8], const sp::Fe* e) {
+    sp::Fe c[2][8], send[2][4];
+    for (int h = 0; h < 2; h++) {
+        for (int j = 0; j < 8; j++) c[h][j] = e[h + 2 * j];
+        sp::half_crt_local(c[h]);
+        sp::half_crt_send(send[h], c[h], h);
+    }
+    for (int h = 0; h < 2; h++) sp::half_crt_cross(pos[h], c[h], send[1 - h], h);
+}
+static void sp_half_icrt_host(sp::Fe* e, sp::Fe (&pos)[2][8]) {
+    sp::Fe send[2][4], c[2][8];
+    for (int h = 0; h < 2; h++) {
+        sp::half_icrt_first(pos[h], h);
+        sp::half_icrt_send(send[h], pos[h], h);
+    }
+    for (int h = 0; h < 2; h++) {
+        sp::half_icrt_gather(c[h], pos[h], send[1 - h], h);
+        sp::half_icrt_local(c[h]);
+        for (int j = 0; j < 8; j++) e[h + 2 * j] = c[h][j];
+    }
+}
+void hc_sp_crt_half(uint64_t* e) {
+    sp::Fe x[16], pos[2][8]; memcpy(x, e, 512);
+    sp_half_crt_host(pos, x);
+    for (int h = 0; h < 2; h++) for (int q = 0; q < 8; q++) x[8 * h + q] = pos[h][q];
+    memcpy(e, x, 512);
+}
+void hc_sp_icrt_half(uint64_t* e) {
+    sp::Fe x[16], pos[2][8]; memcpy(x, e, 512);
+    for (int h = 0; h < 2; h++) for (int q = 0; q < 8; q++) pos[h][q] = x[8 * h + q];
+    sp_half_icrt_host(x, pos);
+    memcpy(e, x, 512);
 }
 
 }  // extern "C"

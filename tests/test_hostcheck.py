@@ -58,6 +58,11 @@ def test_elementwise_against_oracle(hc, name, tag):
         out = np.zeros(w, dtype=np.uint64)
         getattr(hc, "hc_%s_ring_mul" % tag)(_p(ea), _p(eb), _p(out))
         assert np.array_equal(out, want_rm[i * w:(i + 1) * w]), ("ring_mul", i)
+        if tag == "sp":  # two-threads-per-element formulation (sp_half.cuh)
+            x = ea.copy(); hc.hc_sp_crt_half(_p(x))
+            assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt_half", i)
+            x = ea.copy(); hc.hc_sp_icrt_half(_p(x))
+            assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt_half", i)
         if tag == "bb":  # two-threads-per-element formulation used by the fused kernel
             out2 = np.zeros(w, dtype=np.uint64)
             hc.hc_bb_ring_mul_half(_p(ea), _p(eb), _p(out2))
