@@ -294,7 +294,7 @@ SR_D void mont_round_eo(u32 (&X)[L + 1], u32 (&Y)[L + 1], u32& zlo, u32& zhi, co
 
 // r = a * b * 2^-256 mod p (canonical output for canonical inputs)
 SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
-#if defined(__CUDA_ARCH__) && defined(SR_SP_MONT_EO)  // experimental: ptxas spills carry predicates (see profiles/r01_tuning.md)
+#if defined(__CUDA_ARCH__) && !defined(SR_SP_MONT_NO_EO)  // even/odd carry-save rounds (default)
     u32 X[L + 1], Y[L + 1], zlo = 0, zhi = 0, t[L + 1];
 #pragma unroll
     for (int i = 0; i < L + 1; i++) X[i] = Y[i] = 0;
