@@ -13,6 +13,15 @@
 // products need a 64 x 64 multiplication.  Memory holds x * 2^64 mod p (Montgomery); CRT/ICRT are
 // linear so they act on the raw limbs directly, and the slot product's extra 2^-64 = 2^128 is a
 // power of two as well (folded into the 1/8, 1/4 scalings in the fused path).
+//
+// Value discipline.  Intermediate values are WEAK: any u64 congruent to the value mod p.  The
+// primitives below keep that cheap on the GPU (PTX carry chains, no compare/select):
+//   add(a, b), sub(a, b)   a weak, b CANONICAL (< p, or == p)  -> weak      5 instructions
+//   canon(x)               weak -> canonical
+//   mul, mul_pow2<K>       weak inputs -> weak
+// (a + b with b <= p cannot overflow twice: a + b - 2^64 < p, so one conditional +EPS suffices;
+// likewise for the borrow.)  On the host the same functions are plain canonical C, which is a
+// special case of weak, so tests/hostcheck exercises the same call graph.
 #pragma once
 #include "sr_common.cuh"
 #include "sr_consts_gen.cuh"
@@ -30,45 +39,104 @@ constexpr int root_exp(int k) {
     return t[k];
 }
 
-// canonical add / sub / neg (inputs < p)
+SR_HD u64 canon(u64 x) { return x >= P ? x - P : x; }
+
+#if defined(__CUDA_ARCH__)
+SR_D u64 mk64(u32 lo, u32 hi) { return (u64)lo | ((u64)hi << 32); }
+// a weak, b canonical -> weak
+SR_D u64 add(u64 a, u64 b) {
+    u32 lo, hi;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "add.cc.u32   %0, %2, %4;\n\t"
+        "addc.cc.u32  %1, %3, %5;\n\t"
+        "addc.u32     m, 0, 0;\n\t"          // m = carry (add-flags are never fed to subc)
+        "sub.cc.u32   %0, %0, m;\n\t"        // + EPS = + 2^32 - 1 when the sum wrapped
+        "subc.u32     %1, %1, 0;\n\t"
+        "add.u32      %1, %1, m;\n\t"
+        "}"
+        : "=&r"(lo), "=&r"(hi)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return mk64(lo, hi);
+}
+SR_D u64 sub(u64 a, u64 b) {
+    u32 lo, hi;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "sub.cc.u32   %0, %2, %4;\n\t"
+        "subc.cc.u32  %1, %3, %5;\n\t"
+        "subc.u32     m, 0, 0;\n\t"          // m = -borrow
+        "sub.cc.u32   %0, %0, m;\n\t"        // - EPS when the difference wrapped
+        "subc.u32     %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(lo), "=&r"(hi)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return mk64(lo, hi);
+}
+// lo + hl * (2^32 - 1) for a 32-bit hl (weak result)
+SR_D u64 add_eps_mul(u64 lo, u32 hl) {
+    u32 r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "mad.lo.cc.u32   %0, %4, 0xFFFFFFFF, %2;\n\t"
+        "madc.hi.cc.u32  %1, %4, 0xFFFFFFFF, %3;\n\t"
+        "addc.u32        m, 0, 0;\n\t"
+        "sub.cc.u32      %0, %0, m;\n\t"
+        "subc.u32        %1, %1, 0;\n\t"
+        "add.u32         %1, %1, m;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"(hl));
+    return mk64(r0, r1);
+}
+// (hi, lo) = 128-bit value -> weak residue.  2^64 = 2^32 - 1, 2^96 = -1 (mod p).
+SR_D u64 reduce128(u64 lo, u64 hi) {
+    const u64 t0 = sub(lo, hi >> 32);  // hi >> 32 < 2^32: canonical
+    return add_eps_mul(t0, (u32)hi);
+}
+SR_D u64 neg(u64 a) { return P - canon(a); }  // weak (p itself for a = 0)
+#else
+// host: canonical arithmetic (a special case of the weak discipline)
 SR_HD u64 add(u64 a, u64 b) {
+    a = canon(a);
     u64 s = a + b;
     bool over = (s < a) | (s >= P);
-    return over ? s + EPS : s;  // s - p == s + EPS (mod 2^64)
+    return over ? s + EPS : s;
 }
 SR_HD u64 sub(u64 a, u64 b) {
+    a = canon(a);
     u64 d = a - b;
-    return (a < b) ? d - EPS : d;  // d + p == d - EPS (mod 2^64)
+    return (a < b) ? d - EPS : d;
 }
-SR_HD u64 neg(u64 a) { return a ? P - a : 0; }
-
-// (hi, lo) = 128-bit value -> canonical residue.  2^64 = 2^32 - 1, 2^96 = -1 (mod p).
 SR_HD u64 reduce128(u64 lo, u64 hi) {
     u64 hh = hi >> 32, hl = hi & EPS;
     u64 t0 = lo - hh;
-    if (lo < hh) t0 -= EPS;          // borrowed 2^64 = EPS
-    u64 t1 = (hl << 32) - hl;        // hl * (2^32 - 1)
+    if (lo < hh) t0 -= EPS;
+    u64 t1 = (hl << 32) - hl;
     u64 r = t0 + t1;
-    if (r < t1) r += EPS;            // carried 2^64 = EPS
+    if (r < t1) r += EPS;
     return r >= P ? r - P : r;
 }
+SR_HD u64 neg(u64 a) { a = canon(a); return a ? P - a : 0; }
+#endif
+
 SR_HD u64 mul(u64 a, u64 b) { return reduce128(a * b, mul64hi(a, b)); }
 
-// x * 2^K mod p for a compile-time K in [0, 192)
+// x * 2^K mod p for a compile-time K in [0, 192); weak in, weak out
 template <int K>
 SR_HD u64 mul_pow2(u64 x) {
     static_assert(K >= 0 && K < 192, "exponent");
     constexpr int KK = K % 96, s = KK % 32, j = KK / 32;
     // v = x << s as 96 bits (v2:v1:v0)
-    u64 lo = x << s;
-    u32 v2 = s ? (u32)(x >> (64 - s)) : 0u;
-    u32 v0 = (u32)lo, v1 = (u32)(lo >> 32);
+    const u64 lo = x << s;
+    const u32 v2 = s ? (u32)(x >> (64 - s)) : 0u;
+    const u32 v0 = (u32)lo, v1 = (u32)(lo >> 32);
     u64 r;
     if (j == 0) {
         r = reduce128(lo, v2);
     } else if (j == 1) {  // v0 2^32 + v1 2^64 - v2
         r = sub(reduce128((u64)v0 << 32, v1), (u64)v2);
-    } else {              // v0 2^64 - v1 - v2 2^32
+    } else {              // v0 2^64 - v1 - v2 2^32   (v2 < 2^31: the subtrahend is canonical)
         r = sub(reduce128(0, v0), (u64)v1 | ((u64)v2 << 32));
     }
     return K >= 96 ? neg(r) : r;
@@ -78,33 +146,39 @@ SR_HD u64 mulw(u64 x) {  // x * ROOTS_OF_UNITY_24[K]
     return mul_pow2<root_exp(K)>(x);
 }
 
+// (a, b) <- (a + w b, a - w b); a, b weak.  For w = -2^e the two outputs simply swap roles.
 template <int LO, int SPAN, int K>
 SR_HD void bfly(u64 (&c)[D]) {
+    constexpr int E = root_exp(K);
 #pragma unroll
     for (int i = 0; i < SPAN; i++) {
-        u64 a = c[LO + i], t = mulw<K>(c[LO + SPAN + i]);
-        c[LO + i] = add(a, t);
-        c[LO + SPAN + i] = sub(a, t);
+        const u64 a = c[LO + i], t = canon(mul_pow2<E % 96>(c[LO + SPAN + i]));
+        c[LO + i] = (E >= 96) ? sub(a, t) : add(a, t);
+        c[LO + SPAN + i] = (E >= 96) ? add(a, t) : sub(a, t);
     }
 }
+// (a, b) <- (a + b, w (a - b)); w = -2^e turns a - b into b - a
 template <int LO, int SPAN, int K>
 SR_HD void ibfly(u64 (&c)[D]) {
+    constexpr int E = root_exp(K);
 #pragma unroll
     for (int i = 0; i < SPAN; i++) {
-        u64 a = c[LO + i], b = c[LO + SPAN + i];
-        c[LO + i] = add(a, b);
-        c[LO + SPAN + i] = mulw<K>(sub(a, b));
+        const u64 a = c[LO + i], b = c[LO + SPAN + i];
+        const u64 ca = canon(a), cb = canon(b);
+        c[LO + i] = add(a, cb);
+        c[LO + SPAN + i] = mul_pow2<E % 96>((E >= 96) ? sub(b, ca) : sub(a, cb));
     }
 }
 
-// ntt.rs:146-225
+// ntt.rs:146-225.  Input canonical (memory) or weak; output weak.
 SR_HD void crt_stages(u64 (&c)[D]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        u64 a = c[i], b = c[12 + i];
-        u64 z = mulw<4>(b);
-        c[i] = add(a, z);
-        c[12 + i] = sub(add(a, b), z);
+        // zeta = ROOTS_OF_UNITY_24[4] = 2^160 = -2^64:  z = -z'  with z' = 2^64 b
+        const u64 a = c[i], b = canon(c[12 + i]);
+        const u64 zp = canon(mul_pow2<64>(b));
+        c[i] = sub(a, zp);                 // a + zeta b
+        c[12 + i] = add(add(a, b), zp);    // a + b - zeta b
     }
     bfly<0, 6, 2>(c);
     bfly<12, 6, 10>(c);
@@ -114,7 +188,7 @@ SR_HD void crt_stages(u64 (&c)[D]) {
     bfly<18, 3, 11>(c);
 }
 
-// ntt.rs:250-318.  EXTRA: additional power of two folded into the 1/8 and 1/4 scalings.
+// ntt.rs:250-318.  EXTRA: additional power of two folded into the 1/8 and 1/4 scalings.  Output weak.
 template <int EXTRA>
 SR_HD void icrt_stages(u64 (&c)[D]) {
     ibfly<0, 3, 23>(c);
@@ -125,9 +199,9 @@ SR_HD void icrt_stages(u64 (&c)[D]) {
     ibfly<12, 6, 14>(c);
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        u64 a = c[i], b = c[12 + i];
-        u64 kd = mul(sub(a, b), (u64)SR_GL_KAPPA);
-        c[i] = mul_pow2<(189 + EXTRA) % 192>(sub(add(a, b), kd));
+        const u64 a = c[i], cb = canon(c[12 + i]);
+        const u64 kd = canon(mul(sub(a, cb), (u64)SR_GL_KAPPA));
+        c[i] = mul_pow2<(189 + EXTRA) % 192>(sub(add(a, cb), kd));
         c[12 + i] = mul_pow2<(190 + EXTRA) % 192>(kd);
     }
 }
@@ -147,28 +221,89 @@ SR_HD void dehomogenize(u64 (&o)[D], const u64 (&c)[D]) {
 #undef NEG
 }
 
+// full transforms: canonical in, canonical out
 SR_HD void crt(u64 (&c)[D]) {
     crt_stages(c);
     u64 o[D];
     homogenize(o, c);
 #pragma unroll
-    for (int i = 0; i < D; i++) c[i] = o[i];
+    for (int i = 0; i < D; i++) c[i] = canon(o[i]);
 }
 SR_HD void icrt(u64 (&c)[D]) {
     u64 o[D];
     dehomogenize(o, c);
     icrt_stages<0>(o);
 #pragma unroll
-    for (int i = 0; i < D; i++) c[i] = o[i];
+    for (int i = 0; i < D; i++) c[i] = canon(o[i]);
 }
 
-// z = x * y in F_p[u]/(u^3 - 2^RHO_EXP), then times 2^POST_EXP.
+#if defined(__CUDA_ARCH__)
+// ---- lazy accumulation of 64 x 64 -> 128-bit products -------------------------------------------
+// The sum is kept UNREDUCED in a 160-bit accumulator held as two interleaved carry-save halves
+// (E: limbs 0..4 takes lo*lo and hi*hi, O: limbs 1..3 takes the two cross products), so every partial
+// product is one IMAD.WIDE.U32 with carry and no modular reduction happens until the end.
+struct Acc {
+    u32 e0, e1, e2, e3, e4, o1, o2, o3;
+};
+SR_D void acc_zero(Acc& A) { A.e0 = A.e1 = A.e2 = A.e3 = A.e4 = A.o1 = A.o2 = A.o3 = 0; }
+SR_D void acc_mad(Acc& A, u64 a, u64 b) {
+    const u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
+    asm("mad.lo.cc.u32   %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32  %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32  %2, %6, %8, %2;\n\t"
+        "madc.hi.cc.u32  %3, %6, %8, %3;\n\t"
+        "addc.u32        %4, %4, 0;\n\t"
+        : "+r"(A.e0), "+r"(A.e1), "+r"(A.e2), "+r"(A.e3), "+r"(A.e4)
+        : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+    asm("mad.lo.cc.u32   %0, %3, %6, %0;\n\t"
+        "madc.hi.cc.u32  %1, %3, %6, %1;\n\t"
+        "addc.u32        %2, %2, 0;\n\t"
+        "mad.lo.cc.u32   %0, %4, %5, %0;\n\t"
+        "madc.hi.cc.u32  %1, %4, %5, %1;\n\t"
+        "addc.u32        %2, %2, 0;\n\t"
+        : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3)
+        : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+}
+// canonical residue of the accumulated value (valid while the true sum is < 2^192)
+SR_D u64 acc_reduce(const Acc& A) {
+    u64 c = (u64)A.e1 + A.o1;
+    const u32 l0 = A.e0, l1 = (u32)c;
+    c = (c >> 32) + (u64)A.e2 + A.o2;
+    const u32 l2 = (u32)c;
+    c = (c >> 32) + (u64)A.e3 + A.o3;
+    const u32 l3 = (u32)c;
+    c = (c >> 32) + (u64)A.e4;
+    const u32 l4 = (u32)c, l5 = (u32)(c >> 32);
+    // 2^128 = -2^32, 2^160 = 1 - 2^32 (mod p); l4 2^32 <= p - 1 and l5, l5 2^32 are canonical
+    u64 r = reduce128(mk64(l0, l1), mk64(l2, l3));
+    r = sub(r, (u64)l4 << 32);
+    r = add(r, (u64)l5);
+    r = sub(r, (u64)l5 << 32);
+    return canon(r);
+}
+#endif
+
+// z = x * y in F_p[u]/(u^3 - 2^RHO_EXP), then times 2^POST_EXP.  Weak in, weak out.
 template <int RHO_EXP, int POST_EXP>
 SR_HD void slot_mul(u64* z, const u64* x, const u64* y) {
-    u64 x0 = x[0], x1 = x[1], x2 = x[2], y0 = y[0], y1 = y[1], y2 = y[2];
-    u64 c0 = add(mul(x0, y0), mul_pow2<RHO_EXP>(add(mul(x1, y2), mul(x2, y1))));
-    u64 c1 = add(add(mul(x0, y1), mul(x1, y0)), mul_pow2<RHO_EXP>(mul(x2, y2)));
-    u64 c2 = add(add(mul(x0, y2), mul(x1, y1)), mul(x2, y0));
+    const u64 x0 = x[0], x1 = x[1], x2 = x[2], y0 = y[0], y1 = y[1], y2 = y[2];
+    u64 c0, c1, c2;
+#if defined(__CUDA_ARCH__)
+    Acc d0, d1, d2, d3, d4;  // the five diagonals of the 3 x 3 product
+    acc_zero(d0); acc_zero(d1); acc_zero(d2); acc_zero(d3); acc_zero(d4);
+    acc_mad(d0, x0, y0);
+    acc_mad(d1, x0, y1); acc_mad(d1, x1, y0);
+    acc_mad(d2, x0, y2); acc_mad(d2, x1, y1); acc_mad(d2, x2, y0);
+    acc_mad(d3, x1, y2); acc_mad(d3, x2, y1);
+    acc_mad(d4, x2, y2);
+    c0 = add(mul_pow2<RHO_EXP>(acc_reduce(d3)), acc_reduce(d0));
+    c1 = add(mul_pow2<RHO_EXP>(acc_reduce(d4)), acc_reduce(d1));
+    c2 = acc_reduce(d2);
+#else
+    c0 = add(mul(x0, y0), mul_pow2<RHO_EXP>(add(mul(x1, y2), mul(x2, y1))));
+    c1 = add(add(mul(x0, y1), mul(x1, y0)), mul_pow2<RHO_EXP>(mul(x2, y2)));
+    c2 = add(add(mul(x0, y2), mul(x1, y1)), mul(x2, y0));
+#endif
     if (POST_EXP != 0) {
         c0 = mul_pow2<POST_EXP>(c0);
         c1 = mul_pow2<POST_EXP>(c1);
@@ -181,6 +316,8 @@ SR_HD void slot_mul(u64* z, const u64* x, const u64* y) {
 SR_HD void ntt_mul(u64 (&a)[D], const u64 (&b)[D]) {
 #pragma unroll
     for (int s = 0; s < 8; s++) slot_mul<root_exp(1), 128>(&a[3 * s], &a[3 * s], &b[3 * s]);
+#pragma unroll
+    for (int i = 0; i < D; i++) a[i] = canon(a[i]);
 }
 
 // Fused unit of the metric without the slot isomorphisms: slot s multiplied directly modulo
@@ -190,6 +327,7 @@ SR_HD void fused_slot(u64 (&bs)[D], const u64* as) {
     constexpr int KS[8] = {1, 13, 7, 19, 5, 17, 11, 23};
     slot_mul<root_exp(KS[S]), 0>(&bs[3 * S], &as[3 * S], &bs[3 * S]);
 }
+// bs <- ring product (coefficient form, canonical); as = crt_stages(a), bs = crt_stages(b)
 SR_HD void fused_mul_icrt(u64 (&bs)[D], const u64* as) {
     fused_slot<0>(bs, as);
     fused_slot<1>(bs, as);
@@ -200,6 +338,8 @@ SR_HD void fused_mul_icrt(u64 (&bs)[D], const u64* as) {
     fused_slot<6>(bs, as);
     fused_slot<7>(bs, as);
     icrt_stages<128>(bs);
+#pragma unroll
+    for (int i = 0; i < D; i++) bs[i] = canon(bs[i]);
 }
 
 }  // namespace gl

@@ -26,10 +26,17 @@ struct GLSlot {
     SR_D static Val load_cached(const u64* p) { Val v; v.c[0] = p[0]; v.c[1] = p[1]; v.c[2] = p[2]; return v; }
     SR_D static void store(u64* p, const Val& v) { p[0] = v.c[0]; p[1] = v.c[1]; p[2] = v.c[2]; }
     SR_D static Val zero() { Val v; v.c[0] = v.c[1] = v.c[2] = 0; return v; }
-    SR_D static Val mul(const Val& a, const Val& b) { Val z; gl::slot_mul<gl::root_exp(1), 128>(z.c, a.c, b.c); return z; }
+    // gl:: arithmetic is weak-form (gl_ring.cuh); values stored in Val are kept canonical
+    SR_D static Val mul(const Val& a, const Val& b) {
+        Val z;
+        gl::slot_mul<gl::root_exp(1), 128>(z.c, a.c, b.c);
+#pragma unroll
+        for (int i = 0; i < 3; i++) z.c[i] = gl::canon(z.c[i]);
+        return z;
+    }
     SR_D static void acc(Val& s, const Val& x) {
 #pragma unroll
-        for (int i = 0; i < 3; i++) s.c[i] = gl::add(s.c[i], x.c[i]);
+        for (int i = 0; i < 3; i++) s.c[i] = gl::canon(gl::add(s.c[i], x.c[i]));
     }
 };
 struct BBSlot {
@@ -142,7 +149,7 @@ SR_D u64 gl_acc_reduce(const GLAcc& A) {
     r = gl::sub(r, (u64)l4 << 32);
     r = gl::add(r, (u64)l5);
     r = gl::sub(r, (u64)l5 << 32);
-    return POST ? gl::mul_pow2<POST>(r) : r;
+    return gl::canon(POST ? gl::mul_pow2<POST>(r) : r);
 }
 
 #ifndef SR_GLMV_MINB
@@ -406,16 +413,16 @@ gl_matvec_tma3_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t 
         if (row0 + r >= nrows) break;
         const u64 ra = gl_acc_reduce<0>(accA[r]), rb = gl_acc_reduce<0>(accB[r]);
         u64 c;
-        if (part == 0) c = gl::add(ra, gl::mul_pow2<gl::root_exp(1)>(rb));
-        else if (part == 1) c = gl::add(rb, gl::mul_pow2<gl::root_exp(1)>(ra));
+        if (part == 0) c = gl::add(gl::mul_pow2<gl::root_exp(1)>(rb), ra);
+        else if (part == 1) c = gl::add(gl::mul_pow2<gl::root_exp(1)>(ra), rb);
         else c = gl::add(ra, rb);
-        red[slot][part] = gl::mul_pow2<128>(c);  // Montgomery layout: extra 2^-64 = 2^128
+        red[slot][part] = gl::canon(gl::mul_pow2<128>(c));  // Montgomery layout: extra 2^-64 = 2^128
         __syncthreads();
         if (threadIdx.x < S::SLOTS * 3) {  // 24 threads: (slot index s8, coefficient k)
             const int s8 = threadIdx.x / 3, k = threadIdx.x - 3 * s8;
             u64 acc = 0;
             for (int q = s8; q < GL3_SLOTS; q += S::SLOTS) acc = gl::add(acc, red[q][k]);
-            partial[((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + s8 * 3 + k] = acc;
+            partial[((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + s8 * 3 + k] = gl::canon(acc);
         }
         __syncthreads();
     }
