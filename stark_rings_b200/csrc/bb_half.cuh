@@ -61,8 +61,14 @@ SR_HD void half_crt(u32 (&x)[36], const u32* row, const HalfConsts& K) {
         for (int t = 0; t < 4; t++) { a[t] = row[4 * j + t]; b[t] = row[36 + 4 * j + t]; }
 #endif
 #pragma unroll
-        for (int t = 0; t < 4; t++)  // a + c1 b = red(a 2^32 + b c1'), both products < p^2
+        for (int t = 0; t < 4; t++) {
+#ifdef SR_BB_STAGE1_FUSED
+            // a + c1 b = red(a 2^32 + b c1'), both products < p^2  (3 wide multiply-adds)
             x[4 * j + t] = red((u64)a[t] * R32 + (u64)b[t] * K.c1);
+#else
+            x[4 * j + t] = add(a[t], mulc(b[t], K.c1));  // 2 wide multiply-adds + 3 ALU
+#endif
+        }
     }
 #pragma unroll
     for (int i = 0; i < 18; i++) {

@@ -26,6 +26,21 @@ bb_ring_mul_half_kernel(const u64* a, const u64* b, u64* out, size_t n) {
         stage_in<R, T>(sA, a + e0 * R::WORDS64, ne);
         stage_in<R, T>(sB, b + e0 * R::WORDS64, ne);
         __syncthreads();
+#ifdef SR_BB_L2_PREFETCH  // tried in round 1: no measurable effect (profiles/r01_tuning.md)
+        {   // pull the CTA's next tile into L2 while this one is being multiplied
+            const size_t nt = tile + gridDim.x;
+            if (nt < ntiles) {
+                const size_t ne2 = (n - nt * TE < (size_t)TE) ? (n - nt * TE) : (size_t)TE;
+                const size_t lines = ne2 * R::WORDS64 * 8 / 128;  // 576 B per element: 4.5 lines
+                const char* pa = reinterpret_cast<const char*>(a + nt * TE * R::WORDS64);
+                const char* pb = reinterpret_cast<const char*>(b + nt * TE * R::WORDS64);
+                for (size_t l = threadIdx.x; l < lines; l += T) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + l * 128));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + l * 128));
+                }
+            }
+        }
+#endif
         u32 A[36], B[36], Y[36];
         bb::half_crt(A, sA + el * R::ROW, K);
         bb::half_crt(B, sB + el * R::ROW, K);
