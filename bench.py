@@ -26,6 +26,16 @@ ELEM_BYTES = {"bb": 576, "gl": 192, "sp": 512}
 P = {"bb": 2013265921, "gl": 18446744069414584321}
 
 
+def measured_traffic(tag, workload, log2n):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f).get("%s:%s:%d" % (tag, workload, log2n))
+        return None if t is None else t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -102,6 +112,24 @@ def gen_raw_device(torch, tag, n, seed, device):
     return x
 
 
+def make_config(args, world):
+    """metric / unit / config shared by both arms (ours and --impl reference)."""
+    tag = args.ring
+    n = 1 << args.log2n
+    if args.workload == "ringmul":
+        cfg = {"workload": "%s ring: batched CRT->slot mul->ICRT on 2^%d elements per GPU" % (RING_NAMES[tag], args.log2n),
+               "ring": RING_NAMES[tag], "log2_elements_per_gpu": args.log2n,
+               "l2": "inputs >> L2 (no flush needed)" if n * ELEM_BYTES[tag] > (256 << 20) else "inputs fit L2",
+               "layout": "reference layout: u64 Montgomery limbs, %d B per element" % ELEM_BYTES[tag]}
+        return "ring muls/sec (CRT->mul->ICRT)", "ring_mul/s", cfg
+    cfg = {"workload": "%s commit: %d x 2^%d ring matrix x vector, columns sharded over %d GPU(s)" % (
+               RING_NAMES[tag], args.kappa, args.log2n, world),
+           "ring": RING_NAMES[tag], "log2_columns": args.log2n, "kappa": args.kappa,
+           "l2": "matrix >> L2" if args.kappa * n * ELEM_BYTES[tag] > (256 << 20) else "matrix fits L2",
+           "layout": "reference layout: u64 Montgomery limbs, %d B per element" % ELEM_BYTES[tag]}
+    return "commits/sec (kappa x m ring matrix x vector)", "commit/s", cfg
+
+
 def cpu_reference_rate(tag, sample_elems, threads, repeats=1):
     """ring muls/s of the C restatement (oracle/sr_oracle.c, -march=native) on this host."""
     import numpy as np
@@ -122,32 +150,53 @@ def cpu_reference_rate(tag, sample_elems, threads, repeats=1):
 
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (C restatement: the Rust crate cannot be
-    built here) on the box's host cores.  Rank 0 only."""
+    built here) on the box's host cores, all threads, same metric / unit / config as our arm.
+    Each step is a bounded sample of the workload.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    import numpy as np
+    from oracle import c_oracle as C
+    from tests.util import rand_raw
     tag = args.ring
     cores = os.cpu_count() or 1
-    sample = min(1 << args.log2n, args.cpu_sample)
+    metric, unit, cfg = make_config(args, world)
     times = []
-    for i in range(args.warmup + args.steps):
-        rate, dt, kind = cpu_reference_rate(tag, sample, cores)
-        if i >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    value = sample / (ms / 1e3)
+    if args.workload == "ringmul":
+        sample = min(1 << args.log2n, args.cpu_sample)
+        for i in range(args.warmup + args.steps):
+            rate, dt, kind = cpu_reference_rate(tag, sample, cores)
+            if i >= args.warmup:
+                times.append(dt)
+        ms = 1e3 * sum(times) / len(times)
+        value = sample / (ms / 1e3)
+        what = "%d elements per step" % sample
+    else:
+        # commit: a bounded number of columns; the reference parallelises over the kappa rows only
+        name = RING_NAMES[tag]
+        lib, kind = C.lib_native()
+        m = min(1 << args.log2n, 1 << 16)
+        rows = [rand_raw(name, m, 40 + i, edge=False) for i in range(args.kappa)]
+        v = rand_raw(name, m, 50, edge=False)
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            C.matvec(name, rows, v, threads=min(cores, args.kappa), L=lib)
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        ms_sample = 1e3 * sum(times) / len(times)
+        ms = ms_sample * ((1 << args.log2n) / m)  # scaled to the full column count
+        value = 1e3 / ms
+        what = "%d of 2^%d columns per step (time scaled linearly), %d row threads" % (m, args.log2n, min(cores, args.kappa))
     line = {
-        "impl": "reference", "metric": "ring muls/sec (CRT->mul->ICRT)", "value": value, "unit": "ring_mul/s",
+        "impl": "reference", "metric": metric, "value": value, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64" if tag != "bb" else "u32",
-        "data": "synthetic",
-        "config": {"workload": "%s ring: batched CRT->slot mul->ICRT on 2^%d elements" % (RING_NAMES[tag], args.log2n),
-                   "ring": RING_NAMES[tag], "log2_elements_per_gpu": args.log2n,
-                   "note": "CPU arm: each step is a bounded sample of %d elements of that workload" % sample},
-        "cpu_baseline": {"value": value, "unit": "ring_mul/s", "cores": cores, "kind": "port",
-                         "sample": "%d elements per step, %s build of oracle/sr_oracle.c (C restatement of the "
-                                   "reference algorithm; the Rust crate cannot be built in this image)" % (sample, kind)},
-        "e2e": {"value": value, "unit": "ring_mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": "strong" if args.workload == "commit" else "weak", "vs_baseline": None,
+        "dtype": "u32" if tag == "bb" else "u64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
+                         "sample": "%s, %s build of oracle/sr_oracle.c (C restatement of the reference algorithm; "
+                                   "the Rust crate cannot be built in this image: no cargo/rustc)" % (what, kind)},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
@@ -215,6 +264,7 @@ def main():
 
     n = 1 << args.log2n
     line = {}
+    metric, unit, config = make_config(args, world)
     if args.workload == "ringmul":
         a = gen_raw_device(torch, tag, n, 0x5EED ^ (1000 * rank + 1), dev)
         b = gen_raw_device(torch, tag, n, 0x5EED ^ (1000 * rank + 2), dev)
@@ -222,8 +272,6 @@ def main():
         step = lambda: cfg.ring_mul_batch(a, b, out=out, ctx=ctx)
         units_per_step = n
         alg_bytes_per_unit = 3 * ELEM_BYTES[tag]
-        metric, unit = "ring muls/sec (CRT->mul->ICRT)", "ring_mul/s"
-        workload = "%s ring: batched CRT->slot mul->ICRT on 2^%d elements per GPU" % (RING_NAMES[tag], args.log2n)
     else:
         # Goldilocks Ajtai-style commit: kappa x m matrix times vector, columns sharded over ranks
         m_local = n // world
@@ -248,9 +296,6 @@ def main():
             return part
         units_per_step = 1
         alg_bytes_per_unit = (args.kappa * m_local + m_local + args.kappa) * ELEM_BYTES[tag]
-        metric, unit = "commits/sec (kappa x m ring matrix x vector)", "commit/s"
-        workload = "%s commit: %d x 2^%d ring matrix x vector, columns sharded over %d GPU(s)" % (
-            RING_NAMES[tag], args.kappa, args.log2n, world)
 
     # ---- device-resident timing ---------------------------------------------------------------
     for _ in range(args.warmup):
@@ -285,7 +330,7 @@ def main():
     else:
         achieved = alg_bytes_per_unit / (k_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                "traffic": measured_traffic(tag, args.workload, args.log2n), "peak_source": peak_src, "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes_per_unit * (units_per_step if args.workload == "ringmul" else 1)}
 
     # ---- end to end through the C ABI with HOST buffers -----------------------------------------
@@ -340,13 +385,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "u32" if tag == "bb" else "u64", "data": "synthetic",
-            "config": {"workload": workload, "ring": RING_NAMES[tag], "log2_elements_per_gpu": args.log2n,
-                       "l2": "inputs >> L2 (no flush needed)" if n * ELEM_BYTES[tag] > (256 << 20) else "inputs fit L2",
-                       "layout": "reference layout: u64 Montgomery limbs, %d B per element" % ELEM_BYTES[tag]},
+            "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
-        if args.workload == "commit":
-            line["config"]["kappa"] = args.kappa
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
