@@ -46,31 +46,43 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Starts nvidia-smi (20 ms period) and waits until it delivers samples, so that short timed
+        regions are covered; mark_begin()/mark_end() bracket the timed region."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 5.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -78,7 +90,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t) + 0.03]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: use the samples taken under the same load
+            inside = [r for _, r in self.rows]
+            window = "warm-up + timed region (timed region shorter than the 20 ms sampling period)"
+        for r in inside:
             if len(r) < 9:
                 continue
             try:
@@ -91,7 +108,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def gen_raw_device(torch, tag, n, seed, device):
@@ -216,6 +233,7 @@ def main():
     ap.add_argument("--e2e-log2n", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="commit workload, 1 GPU: capture the step in a CUDA graph")
     args = ap.parse_args()
     if args.ring is None:
         args.ring = "gl" if args.workload == "commit" else "bb"
@@ -242,6 +260,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = S.Context(local)
@@ -298,27 +317,53 @@ def main():
         alg_bytes_per_unit = (args.kappa * m_local + m_local + args.kappa) * ELEM_BYTES[tag]
 
     # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    launches_per_step = None
+    if args.workload == "commit" and args.graph and world == 1:
+        # optional, single GPU only: capture the step's kernels in a CUDA graph (the row table is already
+        # resident, see sr_capi.cu).  Measured gain 1% at kappa = 4, m = 2^20; with NCCL in the step the capture
+        # hung in round 1, so multi-GPU runs always use eager launches.
+        try:
+            l0 = ctx.kernel_launches
+            step()
+            launches_per_step = ctx.kernel_launches - l0
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            step = graph.replay
+            for _ in range(3):
+                step()
+            config["cuda_graph"] = True
+        except Exception as ex:  # keep the eager path
+            config["cuda_graph"] = "capture failed: %s" % str(ex)[:80]
+            torch.cuda.synchronize()
+        barrier()
     launches0 = ctx.kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = ctx.kernel_launches - launches0
+    if launches == 0 and launches_per_step:  # graph replays do not pass through the launch counter
+        launches = launches_per_step * args.steps
     ms_per_step = total_ms / args.steps
     strong = args.workload == "commit"
     value = (units_per_step * (1 if strong else world)) / (ms_per_step / 1e3)
 
     # roofline of the dominant kernel: its own launches, timed alone with events on the same stream
+    ctx.use_torch_stream()  # (a graph capture leaves the context on the capture stream)
     ktimes = []
     for _ in range(min(args.steps, 5)):
         ctx.timer_start()

@@ -48,6 +48,7 @@ struct sr_ctx {
     size_t mv_scratch_bytes = 0;
     void* mv_rows = nullptr;  // device copy of the row-pointer table
     size_t mv_rows_cap = 0;
+    std::vector<const void*> mv_rows_cached;  // host copy of what mv_rows holds (skip re-upload if unchanged)
 };
 
 namespace {
@@ -182,6 +183,7 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
         if (ctx->mv_rows) cudaFree(ctx->mv_rows);
         ctx->mv_rows = nullptr;
         ctx->mv_rows_cap = 0;
+        ctx->mv_rows_cached.clear();
         CU(cudaMalloc(&ctx->mv_rows, nrows * sizeof(void*)));
         ctx->mv_rows_cap = nrows;
     }
@@ -189,7 +191,16 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
     if (loc == SR_DEVICE) {
         for (size_t i = 0; i < nrows; i++)
             if (!rows[i] || !aligned16(rows[i])) return fail(ctx, SR_ERR_INVALID, "row pointer null or misaligned");
-        CU(cudaMemcpyAsync(ctx->mv_rows, rows, nrows * sizeof(void*), cudaMemcpyHostToDevice, st));
+        // the row table is uploaded only when it changed, so a repeated commit with the same matrix issues
+        // kernels only (and can be captured in a CUDA graph)
+        bool same = ctx->mv_rows_cached.size() == nrows;
+        for (size_t i = 0; same && i < nrows; i++) same = (ctx->mv_rows_cached[i] == (const void*)rows[i]);
+        if (!same) {
+            ctx->mv_rows_cached.assign(rows, rows + nrows);
+            CU(cudaMemcpyAsync(ctx->mv_rows, ctx->mv_rows_cached.data(), nrows * sizeof(void*),
+                               cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        }
         CU(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, v, out, ctx->mv_scratch, st,
                              ctx->sms, &launches));
         ctx->launches += launches;
@@ -228,6 +239,7 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
             CUX(cudaMemcpyAsync(drows[i], rows[i], row_bytes, cudaMemcpyHostToDevice, st));
         }
     }
+    ctx->mv_rows_cached.clear();
     CUX(cudaMemcpyAsync(ctx->mv_rows, drows.data(), nrows * sizeof(void*), cudaMemcpyHostToDevice, st));
     CUX(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, (const u64*)dv, (u64*)dout,
                           ctx->mv_scratch, st, ctx->sms, &launches));
