@@ -213,3 +213,38 @@ def test_large_batch_properties(S, name, n):
     idx = np.r_[0:32, n - 32:n]
     sel = lambda x: np.concatenate([x[i * w:(i + 1) * w] for i in idx])
     assert np.array_equal(sel(host(ab)), C.ring_mul(name, sel(a), sel(b), threads=8))
+
+
+@pytest.mark.parametrize("name,log2n", [("goldilocks", 16), ("babybear", 24), ("stark_prime", 20)])
+def test_baseline_config_sizes_properties(S, name, log2n):
+    """BASELINE.json configs 1-3 at their full sizes (Goldilocks 2^16, BabyBear 2^24, Starknet 2^20), inputs
+    generated on the device: CRT/ICRT round trip, NTT-form product == fused product, commutativity,
+    multiplication by ONE, and an oracle check on a sample of elements."""
+    import torch
+    from bench import gen_raw_device
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    tag = cfg.tag
+    n = 1 << log2n
+    devc = torch.device("cuda", 0)
+    a = gen_raw_device(torch, tag, n, 101, devc)
+    b = gen_raw_device(torch, tag, n, 202, devc)
+    ab = cfg.ring_mul_batch(a, b)
+    assert torch.equal(ab, cfg.ring_mul_batch(b, a))
+    # crt -> slot-wise mul -> icrt through the three separate kernels == fused kernel
+    ta, tb = a.clone(), b.clone()
+    cfg.crt_batch(ta)
+    cfg.crt_batch(tb)
+    cfg.ntt_mul_batch(ta, tb)
+    cfg.icrt_batch(ta)
+    assert torch.equal(ta, ab)
+    del ta
+    cfg.icrt_batch(tb)
+    assert torch.equal(tb, b)
+    del tb
+    one = torch.from_numpy(np.array(O.to_raw(M, [1] + [0] * (M.D - 1)), dtype=np.uint64).view(np.int64)).to(devc)
+    assert torch.equal(cfg.ring_mul_batch(a, one.repeat(n)), a)
+    w = WORDS[name]
+    idx = torch.tensor([0, 1, n // 3, n - 2, n - 1], device=devc)
+    cols = (idx[:, None] * w + torch.arange(w, device=devc)[None, :]).reshape(-1)
+    sa, sb, sab = (host(x[cols]) for x in (a, b, ab))
+    assert np.array_equal(sab, C.ring_mul(name, sa, sb, threads=4))
