@@ -132,6 +132,16 @@ SR_HD u64 mul_pow2(u64 x) {
     const u32 v2 = s ? (u32)(x >> (64 - s)) : 0u;
     const u32 v0 = (u32)lo, v1 = (u32)(lo >> 32);
     u64 r;
+#if defined(__CUDA_ARCH__)
+    // the high part of the shifted value has at most 32 bits: skip the 2^96 term of reduce128
+    if (j == 0) {
+        r = add_eps_mul(lo, v2);                                    // v0 + v1 2^32 + v2 2^64
+    } else if (j == 1) {
+        r = sub(add_eps_mul((u64)v0 << 32, v1), (u64)v2);           // v0 2^32 + v1 2^64 - v2
+    } else {
+        r = sub((u64)v0 * EPS, (u64)v1 | ((u64)v2 << 32));          // v0 2^64 - v1 - v2 2^32; v0 EPS < p
+    }
+#else
     if (j == 0) {
         r = reduce128(lo, v2);
     } else if (j == 1) {  // v0 2^32 + v1 2^64 - v2
@@ -139,6 +149,7 @@ SR_HD u64 mul_pow2(u64 x) {
     } else {              // v0 2^64 - v1 - v2 2^32   (v2 < 2^31: the subtrahend is canonical)
         r = sub(reduce128(0, v0), (u64)v1 | ((u64)v2 << 32));
     }
+#endif
     return K >= 96 ? neg(r) : r;
 }
 template <int K>
@@ -170,12 +181,12 @@ SR_HD void ibfly(u64 (&c)[D]) {
     }
 }
 
-// ntt.rs:146-225.  Input canonical (memory) or weak; output weak.
+// ntt.rs:146-225.  Input CANONICAL (as stored in memory); output weak.
 SR_HD void crt_stages(u64 (&c)[D]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         // zeta = ROOTS_OF_UNITY_24[4] = 2^160 = -2^64:  z = -z'  with z' = 2^64 b
-        const u64 a = c[i], b = canon(c[12 + i]);
+        const u64 a = c[i], b = c[12 + i];
         const u64 zp = canon(mul_pow2<64>(b));
         c[i] = sub(a, zp);                 // a + zeta b
         c[12 + i] = add(add(a, b), zp);    // a + b - zeta b
