@@ -110,6 +110,16 @@ int sr_matvec_partial(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t
 int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t nranks, size_t nrows,
                        uint64_t* out, int loc);
 
+/* ---- coefficient-form helpers next to the hot path (out of place, out != in) ----
+ * sr_reduce_batch replaces CyclotomicConfig::reduce_in_place (goldilocks/mod.rs:75-98, babybear/mod.rs:87-110,
+ * stark_prime/mod.rs:40-47) on a batch: `in` holds polynomials of coeffs_per_poly field elements each
+ * (D <= coeffs_per_poly <= 2D, shorter inputs are the caller's zero padding), `out` receives D per polynomial.
+ * sr_rot_batch replaces Cyclotomic::rot (multiplication by X; goldilocks/mod.rs:138-149, babybear/mod.rs:150-161,
+ * stark_prime/mod.rs:87-95). */
+int sr_reduce_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t in_limbs, size_t coeffs_per_poly,
+                    uint64_t* out, int loc);
+int sr_rot_batch(sr_ctx* ctx, int ring, const uint64_t* in, uint64_t* out, size_t n_limbs, int loc);
+
 /* ---- per-prime entry points (what each model module binds) --------------------------------- */
 #define SR_DECLARE_RING(tag)                                                                          \
     int sr_##tag##_crt_batch(sr_ctx* ctx, uint64_t* buf, size_t n_limbs, int loc);                   \

@@ -25,6 +25,10 @@ def _bind(path):
     L.sro_matvec.argtypes = [ctypes.c_int, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, u64p,
                              ctypes.c_size_t, u64p, ctypes.c_int]
     L.sro_matvec.restype = ctypes.c_int
+    L.sro_reduce.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_size_t, u64p]
+    L.sro_reduce.restype = None
+    L.sro_rot.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, u64p]
+    L.sro_rot.restype = None
     L.sro_crt_stages.argtypes = [ctypes.c_int, u64p]
     L.sro_crt_stages.restype = None
     return L
@@ -95,3 +99,19 @@ def matvec(ring, rows, v, threads=1, L=None):
     out = np.zeros(kappa * w, dtype=np.uint64)
     rc = (L or lib()).sro_matvec(RINGS[ring], arr, kappa, m, _p(v), v.size // w, _p(out), threads)
     return None if rc else out
+
+
+def reduce(ring, polys, coeffs_per_poly, L=None):
+    """polys: flat uint64 array of n polynomials with coeffs_per_poly field elements each -> n ring elements."""
+    w = words(ring)
+    nlimb = 4 if RINGS[ring] == 2 else 1
+    n = polys.size // (coeffs_per_poly * nlimb)
+    out = np.empty(n * w, dtype=np.uint64)
+    (L or lib()).sro_reduce(RINGS[ring], _p(polys), n, coeffs_per_poly, _p(out))
+    return out
+
+
+def rot(ring, a, L=None):
+    out = np.empty_like(a)
+    (L or lib()).sro_rot(RINGS[ring], _p(a), a.size // words(ring), _p(out))
+    return out

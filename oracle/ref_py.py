@@ -289,6 +289,17 @@ def ring_mul(M, a, b):
     return M.icrt(M.ntt_mul(M.crt(a), M.crt(b)))
 
 
+def rot(M, c):
+    """Cyclotomic::rot, multiplication by X (goldilocks/mod.rs:138-149, babybear/mod.rs:150-161,
+    stark_prime/mod.rs:87-95)."""
+    D, p = M.D, M.p
+    last = c[D - 1]
+    out = [(-last) % p] + [x % p for x in c[:D - 1]]
+    if M.name != "stark_prime":
+        out[D // 2] = (out[D // 2] + last) % p
+    return out
+
+
 def ntt_add(M, a, b):
     return [(x + y) % M.p for x, y in zip(a, b)]
 

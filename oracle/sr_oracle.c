@@ -442,6 +442,57 @@ int sro_matvec(int ring, const u64* const* rows, size_t kappa, size_t ncols, con
     return 0;
 }
 
+/* Coefficient-form helpers.  reduce: n polynomials of len field elements (D <= len <= 2D) -> n elements
+ * (goldilocks/mod.rs:75-98, babybear/mod.rs:87-110, stark_prime/mod.rs:40-47). */
+void sro_reduce(int ring, const u64* in, size_t n, size_t len, u64* out) {
+    pthread_once(&once, init_all);
+    if (ring == SRO_SP) {
+        for (size_t e = 0; e < n; e++)
+            for (size_t i = 0; i < 16; i++) {
+                fp4 r, z = {{0, 0, 0, 0}};
+                memcpy(r.v, in + (e * len + i) * 4, 32);
+                if (16 + i < len) memcpy(z.v, in + (e * len + 16 + i) * 4, 32);
+                sp_sub(&r, &r, &z);
+                memcpy(out + (e * 16 + i) * 4, r.v, 32);
+            }
+        return;
+    }
+    const f1_ctx* F = ring == SRO_GL ? &GL : &BB;
+    const size_t D = ring == SRO_GL ? 24 : 72, H = D / 2;
+    for (size_t e = 0; e < n; e++) {
+        const u64* c = in + e * len;
+        for (size_t i = 0; i < H; i++) {
+            u64 r = c[i];
+            if (D + i < len) r = f1_sub(F, r, c[D + i]);
+            if (D + H + i < len) r = f1_sub(F, r, c[D + H + i]);
+            out[e * D + i] = r;
+        }
+        for (size_t i = H; i < D; i++) out[e * D + i] = (H + i < len) ? f1_add(F, c[i], c[H + i]) : c[i];
+    }
+}
+/* rot: multiplication by X (goldilocks/mod.rs:138-149, babybear/mod.rs:150-161, stark_prime/mod.rs:87-95) */
+void sro_rot(int ring, const u64* in, size_t n, u64* out) {
+    pthread_once(&once, init_all);
+    if (ring == SRO_SP) {
+        for (size_t e = 0; e < n; e++) {
+            fp4 last, z = {{0, 0, 0, 0}}, neg;
+            memcpy(last.v, in + (e * 16 + 15) * 4, 32);
+            sp_sub(&neg, &z, &last);
+            memcpy(out + e * 64, neg.v, 32);
+            memcpy(out + e * 64 + 4, in + e * 64, 15 * 32);
+        }
+        return;
+    }
+    const f1_ctx* F = ring == SRO_GL ? &GL : &BB;
+    const size_t D = ring == SRO_GL ? 24 : 72;
+    for (size_t e = 0; e < n; e++) {
+        const u64 last = in[e * D + D - 1];
+        out[e * D] = f1_neg(F, last);
+        for (size_t i = 1; i < D; i++) out[e * D + i] = in[e * D + i - 1];
+        out[e * D + D / 2] = f1_add(F, out[e * D + D / 2], last);
+    }
+}
+
 /* stage-only variants for tests (crt without homogenize) */
 void sro_crt_stages(int ring, u64* e) {
     pthread_once(&once, init_all);

@@ -24,6 +24,8 @@ cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size
                           u64* out, void* scratch, cudaStream_t st, int sms, int* launches);
 cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t nrows, u64* out,
                           cudaStream_t st);
+// coefficient-form helpers (sr_coeff.cu): op 0 = reduce, op 1 = rot
+cudaError_t coeff_launch(int ring, int op, const u64* in, u64* out, size_t n, int len, cudaStream_t st);
 }  // namespace sr
 
 using sr::u64;
@@ -455,6 +457,51 @@ int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t n
     if (e != cudaSuccess) return cuda_fail(ctx, e, "sr_modsum_partials");
     ctx->launches++;
     return SR_OK;
+}
+
+static int coeff_impl(sr_ctx* ctx, int ring, int op, const uint64_t* in, size_t in_limbs, size_t len, uint64_t* out,
+                      int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    const size_t N = (ring == SR_STARK) ? 4 : 1, D = w / N;
+    if (op == 1) len = D;
+    if (len < D || len > 2 * D) return fail(ctx, SR_ERR_BAD_LENGTH, "coefficients per polynomial must be in [D, 2D]");
+    if (in_limbs % (len * N) != 0) return fail(ctx, SR_ERR_BAD_LENGTH, "slice length is not a whole number of polynomials");
+    const size_t n = in_limbs / (len * N);
+    if (n == 0) return SR_OK;
+    if (!in || !out) return fail(ctx, SR_ERR_INVALID, "null buffer");
+    if (in == out) return fail(ctx, SR_ERR_INVALID, "reduce / rot are out of place: out must differ from in");
+    CU(cudaSetDevice(ctx->device));
+    if (loc == SR_DEVICE) {
+        if (!aligned16(in) || !aligned16(out)) return fail(ctx, SR_ERR_INVALID, "device buffers must be 16-byte aligned");
+        CU(sr::coeff_launch(ring, op, in, out, n, (int)len, ctx->stream));
+        ctx->launches++;
+        return SR_OK;
+    }
+    if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    void *din = nullptr, *dout = nullptr;
+    const size_t ib = in_limbs * 8, ob = n * w * 8;
+    cudaError_t e = cudaMalloc(&din, ib);
+    if (e == cudaSuccess) e = cudaMalloc(&dout, ob);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(din, in, ib, cudaMemcpyHostToDevice, ctx->own_stream);
+    if (e == cudaSuccess) e = sr::coeff_launch(ring, op, (const u64*)din, (u64*)dout, n, (int)len, ctx->own_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->own_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);
+    if (din) cudaFree(din);
+    if (dout) cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "coefficient-form helper");
+    ctx->launches++;
+    return SR_OK;
+}
+
+int sr_reduce_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t in_limbs, size_t coeffs_per_poly, uint64_t* out,
+                    int loc) {
+    return coeff_impl(ctx, ring, 0, in, in_limbs, coeffs_per_poly, out, loc);
+}
+int sr_rot_batch(sr_ctx* ctx, int ring, const uint64_t* in, uint64_t* out, size_t n_limbs, int loc) {
+    return coeff_impl(ctx, ring, 1, in, n_limbs, 0, out, loc);
 }
 
 #define SR_DEFINE_RING(tag, RING)                                                                             \

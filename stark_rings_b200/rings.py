@@ -172,6 +172,30 @@ class RingConfig:
         c.check(fn(c.h, pa, pb, na, loc), "ntt_mul_batch")
         return a_inout
 
+    def reduce_batch(self, polys, coeffs_per_poly, ctx=None):
+        """CyclotomicConfig::reduce_in_place on a batch (ring_config.rs:23): polynomials of coeffs_per_poly field
+        elements (D <= coeffs_per_poly <= 2D) -> coefficient-form ring elements (new buffer)."""
+        p, n, loc, dev = _ptr_loc(polys)
+        per = coeffs_per_poly * self.N
+        if coeffs_per_poly < self.D or coeffs_per_poly > 2 * self.D or n % per:
+            raise LengthPanic("reduce: %d limbs is not a batch of polynomials of %d coefficients" % (n, coeffs_per_poly))
+        cnt = n // per
+        out = (np.empty(cnt * self.limbs, dtype=np.uint64) if isinstance(polys, np.ndarray)
+               else torch.empty(cnt * self.limbs, dtype=polys.dtype, device=polys.device))
+        c = self._ctx(dev, ctx)
+        c.check(L.lib.sr_reduce_batch(c.h, self.ring_id, p, n, coeffs_per_poly, _ptr_loc(out)[0], loc), "reduce_batch")
+        return out
+
+    def rot_batch(self, a, ctx=None):
+        """Cyclotomic::rot on a batch: every element multiplied by X (new buffer)."""
+        p, n, loc, dev = _ptr_loc(a)
+        if n % self.limbs:
+            raise LengthPanic("rot: buffer is not a whole number of ring elements")
+        out = np.empty_like(a) if isinstance(a, np.ndarray) else torch.empty_like(a)
+        c = self._ctx(dev, ctx)
+        c.check(L.lib.sr_rot_batch(c.h, self.ring_id, p, _ptr_loc(out)[0], n, loc), "rot_batch")
+        return out
+
     def ring_mul_batch(self, a, b, out=None, ctx=None):
         pa, na, loc, dev = _ptr_loc(a)
         pb, nb, locb, _ = _ptr_loc(b)
@@ -247,6 +271,15 @@ class RqPoly(_RqBase):
         out = RqNTT(self.config, self.data, self.ctx)
         self.data = None
         return out
+
+    def rot(self) -> "RqPoly":
+        """Cyclotomic::rot (models/*/mod.rs): self * X."""
+        return RqPoly(self.config, self.config.rot_batch(self.data, self.ctx), self.ctx)
+
+    @classmethod
+    def from_coeffs_vec(cls, config, polys, coeffs_per_poly, ctx=None) -> "RqPoly":
+        """coeff_form.rs:36-40 / From<Vec<Fp>> (:568-578): reduce mod Phi."""
+        return cls(config, config.reduce_batch(polys, coeffs_per_poly, ctx), ctx)
 
     def __mul__(self, rhs: "RqPoly") -> "RqPoly":
         """coeff_form.rs:250-258 (poly_mul + reduce) == icrt(crt(a) * crt(b)), one fused kernel."""

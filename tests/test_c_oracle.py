@@ -78,3 +78,23 @@ def test_random_batches_and_threads(name):
     assert np.array_equal(C.ring_mul(name, a[: 8 * w].copy(), b[: 8 * w].copy(), threads=2), want_mul)
     # empty batch
     assert C.crt(name, np.zeros(0, dtype=np.uint64)).size == 0
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_reduce_and_rot(name):
+    """SURVEY 8f-2 helpers: reduce_in_place (models/*/mod.rs) and Cyclotomic::rot; rot == multiplication by X."""
+    M = O.MODELS[name]
+    rng = random.Random(12)
+    w = C.words(name)
+    nl = M.limbs
+    for length in (M.D, M.D + 5, 2 * M.D - 1, 2 * M.D):
+        polys = [[rng.randrange(M.p) for _ in range(length)] for _ in range(5)]
+        flat_in = np.array([x for pl in polys for x in O.to_raw(M, pl)], dtype=np.uint64)
+        got = C.reduce(name, flat_in, length)
+        want = flat(M, [M.reduce(pl) for pl in polys])
+        assert np.array_equal(got, want), length
+    elems = rand_elems(M, 6, rng)
+    got = C.rot(name, flat(M, elems))
+    assert np.array_equal(got, flat(M, [O.rot(M, e) for e in elems]))
+    x = [0, 1] + [0] * (M.D - 2)
+    assert O.rot(M, elems[0]) == O.poly_mul(M, elems[0], x)   # models/*/mod.rs test_cyclotomic

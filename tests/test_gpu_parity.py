@@ -248,3 +248,27 @@ def test_baseline_config_sizes_properties(S, name, log2n):
     cols = (idx[:, None] * w + torch.arange(w, device=devc)[None, :]).reshape(-1)
     sa, sb, sab = (host(x[cols]) for x in (a, b, ab))
     assert np.array_equal(sab, C.ring_mul(name, sa, sb, threads=4))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_reduce_and_rot_device(S, name):
+    """SURVEY 8f-2: batched reduce_in_place and Cyclotomic::rot, device and host buffers."""
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    n = 1000
+    for length in (M.D, M.D + 7, 2 * M.D - 1, 2 * M.D):
+        rng = np.random.default_rng(length)
+        per = length * M.limbs
+        src = rand_raw(name, 2 * n, 70 + length)[: n * per].copy()
+        want = C.reduce(name, src, length)
+        assert np.array_equal(host(cfg.reduce_batch(dev(src), length)), want)
+        assert np.array_equal(cfg.reduce_batch(src, length), want)
+    a = rand_raw(name, n, 81)
+    want = C.rot(name, a)
+    p = S.RqPoly(cfg, dev(a))
+    assert np.array_equal(host(p.rot().data), want)
+    assert np.array_equal(cfg.rot_batch(a), want)
+    # rot == multiplication by the monomial X through the fused ring-mul kernel
+    x = np.tile(np.array(O.to_raw(M, [0, 1] + [0] * (M.D - 2)), dtype=np.uint64), n)
+    assert np.array_equal(host(cfg.ring_mul_batch(dev(a), dev(x))), want)
+    with pytest.raises(S.LengthPanic):
+        cfg.reduce_batch(dev(a), M.D - 1)
