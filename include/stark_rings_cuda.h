@@ -120,6 +120,19 @@ int sr_reduce_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t in_limbs, 
                     uint64_t* out, int loc);
 int sr_rot_batch(sr_ctx* ctx, int ring, const uint64_t* in, uint64_t* out, size_t n_limbs, int loc);
 
+/* ---- balanced gadget decomposition feeding the commitment (Goldilocks and BabyBear) ----
+ * sr_gadget_decompose replaces GadgetDecompose for &[R] / Vec<R> with R = RqPoly (balanced_decomposition/mod.rs:163-175,
+ * per element coeff_form.rs:588-606, per coefficient decompose_balanced_in_place mod.rs:62-103): `in` holds n
+ * coefficient-form elements, `out` receives n * padding_size elements, out[j * padding_size + t] = t-th digit element of
+ * in[j]; digits lie in [-b/2, b/2].  The basis b = b_lo + 2^64 b_hi must be even and >= 2 (the reference asserts
+ * this); bases >= 2^62 are not supported.  A decomposition longer than padding_size returns SR_ERR_BAD_LENGTH
+ * (the reference indexes out of bounds and panics).  sr_gadget_recompose is the inverse (mod.rs:177-190):
+ * n * padding_size digit elements -> n elements.  Both are out of place and synchronous. */
+int sr_gadget_decompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint64_t b_lo, uint64_t b_hi,
+                        size_t padding_size, uint64_t* out, int loc);
+int sr_gadget_recompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint64_t b_lo, uint64_t b_hi,
+                        size_t padding_size, uint64_t* out, int loc);
+
 /* ---- per-prime entry points (what each model module binds) --------------------------------- */
 #define SR_DECLARE_RING(tag)                                                                          \
     int sr_##tag##_crt_batch(sr_ctx* ctx, uint64_t* buf, size_t n_limbs, int loc);                   \

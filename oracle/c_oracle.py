@@ -29,6 +29,9 @@ def _bind(path):
     L.sro_reduce.restype = None
     L.sro_rot.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, u64p]
     L.sro_rot.restype = None
+    for name in ("sro_gadget_decompose", "sro_gadget_recompose"):
+        getattr(L, name).argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_size_t, u64p]
+        getattr(L, name).restype = ctypes.c_int
     L.sro_crt_stages.argtypes = [ctypes.c_int, u64p]
     L.sro_crt_stages.restype = None
     return L
@@ -114,4 +117,25 @@ def reduce(ring, polys, coeffs_per_poly, L=None):
 def rot(ring, a, L=None):
     out = np.empty_like(a)
     (L or lib()).sro_rot(RINGS[ring], _p(a), a.size // words(ring), _p(out))
+    return out
+
+
+def gadget_decompose(ring, a, b, pad, L=None):
+    """n elements -> n * pad digit elements; raises IndexError when pad is too small (the reference panics)."""
+    n = a.size // words(ring)
+    out = np.empty(n * pad * words(ring), dtype=np.uint64)
+    rc = (L or lib()).sro_gadget_decompose(RINGS[ring], _p(a), n, b, pad, _p(out))
+    if rc == 1:
+        raise IndexError("padding_size too small")
+    if rc:
+        raise ValueError("unsupported ring or basis")
+    return out
+
+
+def gadget_recompose(ring, digits, b, pad, L=None):
+    n = digits.size // (words(ring) * pad)
+    out = np.empty(n * words(ring), dtype=np.uint64)
+    rc = (L or lib()).sro_gadget_recompose(RINGS[ring], _p(digits), n, b, pad, _p(out))
+    if rc:
+        raise ValueError("unsupported ring")
     return out

@@ -300,6 +300,51 @@ def rot(M, c):
     return out
 
 
+def decompose_balanced(M, x, b, pad):
+    """decompose_balanced_in_place (balanced_decomposition/mod.rs:62-103) of one field element (standard form)
+    into `pad` digits in [-b/2, b/2], returned as field elements; raises IndexError like the reference's
+    out-of-bounds panic when `pad` is too small."""
+    assert b >= 2 and b % 2 == 0
+    p = M.p
+    cur = x - p if x > (p - 1) // 2 else x           # fq_convertible.rs:22-35
+    out = [0] * pad
+    i = 0
+    while True:
+        q = abs(cur) // b * (1 if cur >= 0 else -1)  # Rust: truncating division / remainder
+        rem = cur - q * b
+        if abs(rem) <= b // 2:
+            digit, cur = rem, q
+        else:
+            digit = rem + b if rem < 0 else rem - b
+            cur = q + (-1 if rem < 0 else 1)         # rounded_div(rem, b)
+        out[i] = digit % p                           # IndexError == the reference's panic
+        i += 1
+        if cur == 0:
+            break
+    return out
+
+
+def gadget_decompose(M, elems, b, pad):
+    """GadgetDecompose for &[RqPoly] (mod.rs:163-175; per element coeff_form.rs:588-606)."""
+    out = []
+    for e in elems:
+        digits = [decompose_balanced(M, c, b, pad) for c in e]
+        for t in range(pad):
+            out.append([digits[i][t] for i in range(M.D)])
+    return out
+
+
+def gadget_recompose(M, digit_elems, b, pad):
+    """GadgetRecompose for &[R] (mod.rs:177-190): Horner in the ring."""
+    out = []
+    for j in range(0, len(digit_elems), pad):
+        acc = [0] * M.D
+        for d in reversed(digit_elems[j:j + pad]):
+            acc = [(a * b + x) % M.p for a, x in zip(acc, d)]
+        out.append(acc)
+    return out
+
+
 def ntt_add(M, a, b):
     return [(x + y) % M.p for x, y in zip(a, b)]
 

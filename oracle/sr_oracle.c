@@ -493,6 +493,51 @@ void sro_rot(int ring, const u64* in, size_t n, u64* out) {
     }
 }
 
+/* Balanced gadget decomposition (balanced_decomposition/mod.rs:62-103,163-175, coeff_form.rs:588-606),
+ * Fp64 rings only.  in: n elements; out: n * pad elements.  Returns 1 if a decomposition does not fit in pad digits
+ * (the reference panics), 2 for an unsupported ring / basis. */
+int sro_gadget_decompose(int ring, const u64* in, size_t n, u64 b, size_t pad, u64* out) {
+    pthread_once(&once, init_all);
+    if (ring == SRO_SP || b < 2 || (b & 1) || b >= (1ull << 62)) return 2;
+    const f1_ctx* F = ring == SRO_GL ? &GL : &BB;
+    const size_t D = ring == SRO_GL ? 24 : 72;
+    const long long B = (long long)b, BH = B / 2;
+    int overflow = 0;
+    for (size_t j = 0; j < n; j++)
+        for (size_t i = 0; i < D; i++) {
+            u64 x = f1_mul(F, in[j * D + i], 1);  /* out of Montgomery form */
+            long long cur = x > (F->p - 1) / 2 ? (long long)(x - F->p) : (long long)x;
+            size_t t = 0;
+            for (; t < pad; t++) {
+                long long rem = cur % B, q = cur / B, digit;
+                if ((rem < 0 ? -rem : rem) <= BH) { digit = rem; cur = q; }
+                else { digit = rem < 0 ? rem + B : rem - B; cur = q + (rem < 0 ? -1 : 1); }
+                u64 mag = (u64)(digit < 0 ? -digit : digit) % F->p;
+                u64 dstd = (digit < 0 && mag) ? F->p - mag : mag;
+                out[((j * pad + t) * D) + i] = f1_mul(F, dstd, F->r2);
+                if (cur == 0) { t++; break; }
+            }
+            if (cur != 0) overflow = 1;
+            for (; t < pad; t++) out[((j * pad + t) * D) + i] = 0;
+        }
+    return overflow;
+}
+/* GadgetRecompose (mod.rs:177-190): in holds n * pad digit elements, out n elements. */
+int sro_gadget_recompose(int ring, const u64* in, size_t n, u64 b, size_t pad, u64* out) {
+    pthread_once(&once, init_all);
+    if (ring == SRO_SP) return 2;
+    const f1_ctx* F = ring == SRO_GL ? &GL : &BB;
+    const size_t D = ring == SRO_GL ? 24 : 72;
+    const u64 bm = f1_mul(F, b % F->p, F->r2);
+    for (size_t j = 0; j < n; j++)
+        for (size_t i = 0; i < D; i++) {
+            u64 acc = 0;
+            for (size_t t = pad; t-- > 0;) acc = f1_add(F, f1_mul(F, acc, bm), in[((j * pad + t) * D) + i]);
+            out[j * D + i] = acc;
+        }
+    return 0;
+}
+
 /* stage-only variants for tests (crt without homogenize) */
 void sro_crt_stages(int ring, u64* e) {
     pthread_once(&once, init_all);

@@ -26,6 +26,9 @@ cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t n
                           cudaStream_t st);
 // coefficient-form helpers (sr_coeff.cu): op 0 = reduce, op 1 = rot
 cudaError_t coeff_launch(int ring, int op, const u64* in, u64* out, size_t n, int len, cudaStream_t st);
+// balanced gadget decomposition / recomposition (sr_decomp.cu): op 0 = decompose, op 1 = recompose
+cudaError_t decomp_launch(int ring, int op, const u64* in, u64* out, size_t n, unsigned long long b, u64 b_std, int pad,
+                          int* overflow, cudaStream_t st);
 }  // namespace sr
 
 using sr::u64;
@@ -502,6 +505,66 @@ int sr_reduce_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t in_limbs, 
 }
 int sr_rot_batch(sr_ctx* ctx, int ring, const uint64_t* in, uint64_t* out, size_t n_limbs, int loc) {
     return coeff_impl(ctx, ring, 1, in, n_limbs, 0, out, loc);
+}
+
+static int decomp_impl(sr_ctx* ctx, int ring, int op, const uint64_t* in, size_t in_limbs, uint64_t b_lo, uint64_t b_hi,
+                       size_t pad, uint64_t* out, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ring != SR_GOLDILOCKS && ring != SR_BABYBEAR)
+        return fail(ctx, SR_ERR_INVALID, "gadget (de/re)composition is implemented for the Fp64 rings only");
+    // decompose_balanced_in_place asserts: basis not 0 or 1, and even (mod.rs:63-69)
+    if (b_hi != 0 || b_lo < 2 || (b_lo & 1) || b_lo >= (1ull << 62))
+        return fail(ctx, SR_ERR_INVALID, "decomposition basis must be even, >= 2 and < 2^62");
+    if (pad == 0 || pad > (1u << 20)) return fail(ctx, SR_ERR_INVALID, "padding size out of range");
+    const size_t w = elem_limbs(ring);
+    const size_t in_per = (op == 0) ? w : w * pad;
+    if (in_limbs % in_per != 0) return fail(ctx, SR_ERR_BAD_LENGTH, "slice length is not a whole number of elements");
+    const size_t n = in_limbs / in_per;
+    if (n == 0) return SR_OK;
+    if (!in || !out || in == out) return fail(ctx, SR_ERR_INVALID, "null or aliased buffer");
+    const uint64_t p = (ring == SR_GOLDILOCKS) ? 0xFFFFFFFF00000001ull : 2013265921ull;
+    const uint64_t b_std = b_lo % p;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
+    int* dflag = nullptr;
+    CU(cudaMalloc(&dflag, sizeof(int)));
+    cudaError_t e = cudaMemsetAsync(dflag, 0, sizeof(int), st);
+    void *din = nullptr, *dout = nullptr;
+    const size_t ib = in_limbs * 8, ob = (op == 0 ? n * pad : n) * w * 8;
+    const u64* kin = in;
+    u64* kout = out;
+    if (loc == SR_HOST) {
+        if (e == cudaSuccess) e = cudaMalloc(&din, ib);
+        if (e == cudaSuccess) e = cudaMalloc(&dout, ob);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(din, in, ib, cudaMemcpyHostToDevice, st);
+        kin = (const u64*)din;
+        kout = (u64*)dout;
+    } else if (loc != SR_DEVICE) {
+        cudaFree(dflag);
+        return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    }
+    if (e == cudaSuccess) e = sr::decomp_launch(ring, op, kin, kout, n, b_lo, b_std, (int)pad, dflag, st);
+    if (e == cudaSuccess && loc == SR_HOST) e = cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, st);
+    int flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the overflow flag makes this call synchronous
+    cudaFree(dflag);
+    if (din) cudaFree(din);
+    if (dout) cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "gadget (de/re)composition");
+    ctx->launches++;
+    if (flag) return fail(ctx, SR_ERR_BAD_LENGTH, "padding_size too small for the decomposition (the reference panics)");
+    return SR_OK;
+}
+
+int sr_gadget_decompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint64_t b_lo, uint64_t b_hi,
+                        size_t padding_size, uint64_t* out, int loc) {
+    return decomp_impl(ctx, ring, 0, in, n_limbs, b_lo, b_hi, padding_size, out, loc);
+}
+int sr_gadget_recompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint64_t b_lo, uint64_t b_hi,
+                        size_t padding_size, uint64_t* out, int loc) {
+    return decomp_impl(ctx, ring, 1, in, n_limbs, b_lo, b_hi, padding_size, out, loc);
 }
 
 #define SR_DEFINE_RING(tag, RING)                                                                             \

@@ -196,6 +196,29 @@ class RingConfig:
         c.check(L.lib.sr_rot_batch(c.h, self.ring_id, p, _ptr_loc(out)[0], n, loc), "rot_batch")
         return out
 
+    def _gadget(self, fn, buf, b, padding_size, grow, ctx):
+        p, n, loc, dev = _ptr_loc(buf)
+        per = self.limbs if grow else self.limbs * padding_size
+        if padding_size < 1 or n % per:
+            raise LengthPanic("gadget (de/re)composition: buffer is not a whole number of elements")
+        cnt = (n // per) * (padding_size if grow else 1) * self.limbs
+        out = (np.empty(cnt, dtype=np.uint64) if isinstance(buf, np.ndarray)
+               else torch.empty(cnt, dtype=buf.dtype, device=buf.device))
+        c = self._ctx(dev, ctx)
+        c.check(fn(c.h, self.ring_id, p, n, b & 0xFFFFFFFFFFFFFFFF, b >> 64, padding_size, _ptr_loc(out)[0], loc),
+                "gadget_decompose" if grow else "gadget_recompose")
+        return out
+
+    def gadget_decompose(self, buf, b, padding_size, ctx=None):
+        """GadgetDecompose for &[RqPoly] (balanced_decomposition/mod.rs:163-175): n coefficient-form elements ->
+        n * padding_size digit elements (digits in [-b/2, b/2]).  Too small a padding_size raises LengthPanic
+        (the reference panics)."""
+        return self._gadget(L.lib.sr_gadget_decompose, buf, b, padding_size, True, ctx)
+
+    def gadget_recompose(self, buf, b, padding_size, ctx=None):
+        """GadgetRecompose for &[R] (mod.rs:177-190)."""
+        return self._gadget(L.lib.sr_gadget_recompose, buf, b, padding_size, False, ctx)
+
     def ring_mul_batch(self, a, b, out=None, ctx=None):
         pa, na, loc, dev = _ptr_loc(a)
         pb, nb, locb, _ = _ptr_loc(b)

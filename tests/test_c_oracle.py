@@ -98,3 +98,45 @@ def test_reduce_and_rot(name):
     assert np.array_equal(got, flat(M, [O.rot(M, e) for e in elems]))
     x = [0, 1] + [0] * (M.D - 2)
     assert O.rot(M, elems[0]) == O.poly_mul(M, elems[0], x)   # models/*/mod.rs test_cyclotomic
+
+
+def test_gadget_decompose_reference_kat():
+    """balanced_decomposition/mod.rs:470-514 (test_gadget_decompose / test_gadget_recompose): 15 and -15 in
+    basis 2, padding 4 -> digits (1,1,1,1) / (-1,-1,-1,-1) in every coefficient."""
+    M = O.GOLDILOCKS
+    elems = [[15] * 24, [M.p - 15] * 24]
+    want = [[1] * 24] * 4 + [[M.p - 1] * 24] * 4
+    assert O.gadget_decompose(M, elems, 2, 4) == want
+    assert O.gadget_recompose(M, want, 2, 4) == elems
+    got = C.gadget_decompose("goldilocks", flat(M, elems), 2, 4)
+    assert np.array_equal(got, flat(M, want))
+    assert np.array_equal(C.gadget_recompose("goldilocks", got, 2, 4), flat(M, elems))
+
+
+@pytest.mark.parametrize("name", ["goldilocks", "babybear"])
+@pytest.mark.parametrize("b", [2, 4, 8, 16, 32, 1 << 16, 10, 1 << 40])
+def test_gadget_decompose_properties(name, b):
+    """mod.rs:405-468: every digit within [-b/2, b/2]; recompose(decompose(v)) == v; C == Python."""
+    import math
+    M = O.MODELS[name]
+    rng = random.Random(b)
+    pad = int(math.log(M.p, b)) + 2
+    elems = rand_elems(M, 5, rng)
+    elems[0] = [0] * M.D
+    elems[1] = [M.p - 1] * M.D
+    elems[2] = [(M.p - 1) // 2] * M.D
+    elems[3] = [(M.p - 1) // 2 + 1] * M.D
+    d = O.gadget_decompose(M, elems, b, pad)
+    for de in d:
+        for x in de:
+            s = x - M.p if x > (M.p - 1) // 2 else x
+            assert abs(s) <= b // 2
+    assert O.gadget_recompose(M, d, b, pad) == elems
+    got = C.gadget_decompose(name, flat(M, elems), b, pad)
+    assert np.array_equal(got, flat(M, d))
+    assert np.array_equal(C.gadget_recompose(name, got, b, pad), flat(M, elems))
+    if b < M.p:  # one digit cannot hold (p-1)/2
+        with pytest.raises(IndexError):
+            O.gadget_decompose(M, elems, b, 1)
+        with pytest.raises(IndexError):
+            C.gadget_decompose(name, flat(M, elems), b, 1)

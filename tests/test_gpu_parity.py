@@ -272,3 +272,37 @@ def test_reduce_and_rot_device(S, name):
     assert np.array_equal(host(cfg.ring_mul_batch(dev(a), dev(x))), want)
     with pytest.raises(S.LengthPanic):
         cfg.reduce_batch(dev(a), M.D - 1)
+
+
+@pytest.mark.parametrize("name", ["goldilocks", "babybear"])
+@pytest.mark.parametrize("b,pad", [(2, 66), (4, 34), (16, 18), (1 << 16, 5), (10, 21)])
+def test_gadget_decompose_device(S, name, b, pad):
+    """balanced gadget decomposition / recomposition vs the oracle, device and host buffers, and the
+    decompose -> CRT -> commit chain it feeds."""
+    cfg = S.CONFIGS[name]
+    if name == "babybear" and b == 2:
+        pad = 34
+    n = 300
+    a = rand_raw(name, n, 900 + b)
+    want = C.gadget_decompose(name, a, b, pad)
+    got = cfg.gadget_decompose(dev(a), b, pad)
+    assert np.array_equal(host(got), want)
+    assert np.array_equal(cfg.gadget_decompose(a, b, pad), want)
+    back = cfg.gadget_recompose(got, b, pad)
+    assert np.array_equal(host(back), a)
+    assert np.array_equal(cfg.gadget_recompose(want, b, pad), a)
+    with pytest.raises(S.LengthPanic):
+        cfg.gadget_decompose(dev(a), b, 1)
+    with pytest.raises(S.StarkRingsError):
+        cfg.gadget_decompose(dev(a), 3, pad)  # odd basis: the reference asserts
+
+
+def test_gadget_decompose_reference_kat_device(S):
+    """balanced_decomposition/mod.rs:470-514 on the GPU."""
+    cfg, M = S.CONFIGS["goldilocks"], O.GOLDILOCKS
+    elems = np.array([w for e in ([15] * 24, [M.p - 15] * 24) for w in O.to_raw(M, e)], dtype=np.uint64)
+    want = np.array([w for e in ([[1] * 24] * 4 + [[M.p - 1] * 24] * 4) for w in O.to_raw(M, e)], dtype=np.uint64)
+    assert np.array_equal(host(cfg.gadget_decompose(dev(elems), 2, 4)), want)
+    assert np.array_equal(host(cfg.gadget_recompose(dev(want), 2, 4)), elems)
+    with pytest.raises(S.StarkRingsError):
+        S.CONFIGS["stark_prime"].gadget_decompose(dev(rand_raw("stark_prime", 2, 1)), 2, 300)
