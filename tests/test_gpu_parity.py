@@ -306,3 +306,24 @@ def test_gadget_decompose_reference_kat_device(S):
     assert np.array_equal(host(cfg.gadget_recompose(dev(want), 2, 4)), elems)
     with pytest.raises(S.StarkRingsError):
         S.CONFIGS["stark_prime"].gadget_decompose(dev(rand_raw("stark_prime", 2, 1)), 2, 300)
+
+
+@pytest.mark.parametrize("name", ["goldilocks", "babybear"])
+def test_decompose_crt_commit_chain_on_device(S, name):
+    """The pipeline the hot path serves (decompose -> CRT -> commit) without leaving the device, against the
+    oracle composing the same three steps; plus linearity: A * recompose-weights recovers A * crt(w)."""
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    w = WORDS[name]
+    n_wit, b, pad, kappa = 40, 1 << 8, 9 if name == "goldilocks" else 5, 3
+    wit = rand_raw(name, n_wit, 321)
+    m = n_wit * pad
+    rows = [rand_raw(name, m, 400 + i) for i in range(kappa)]
+    # oracle
+    dec = C.gadget_decompose(name, wit, b, pad)
+    want = C.matvec(name, rows, C.crt(name, dec.copy(), threads=4), threads=4)
+    # device
+    d = cfg.gadget_decompose(dev(wit), b, pad)
+    v = S.RqPoly(cfg, d).crt()
+    A = S.Matrix([S.RqNTT(cfg, dev(r)) for r in rows])
+    y = A.try_mul_vec(v)
+    assert np.array_equal(host(y.data), want)
