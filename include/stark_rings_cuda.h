@@ -133,6 +133,29 @@ int sr_gadget_decompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limb
 int sr_gadget_recompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint64_t b_lo, uint64_t b_hi,
                         size_t padding_size, uint64_t* out, int loc);
 
+/* ---- the callers' other linear maps over NTT-form elements ------------------------------
+ * sr_sparse_matvec replaces SparseMatrix<R>::checked_mul_vec / try_mul_vec / Mul<&[R]> with R = RqNTT
+ * (linear_algebra/src/sparse_matrix.rs:201-217, 278-286): out[i] = sum over (r, j) in coeffs[i] of r * v[j].
+ * The matrix crosses the boundary as the CSR image of coeffs: Vec<Vec<(R, usize)>> (sparse_matrix.rs:17-21):
+ * row_ptr[nrows + 1] entry offsets (row_ptr[0] = 0, non-decreasing, row_ptr[nrows] = nnz), col_idx[nnz], and vals =
+ * nnz NTT-form elements in row order; all of them, v and out live in `loc`.  ncols != v.len() returns
+ * SR_ERR_BAD_LENGTH (the reference returns None / DifferentLengths(ncols, v.len())); a column index >= ncols
+ * returns SR_ERR_INVALID (the reference panics on v[*i]).  Synchronous (the index check reads a device flag). */
+int sr_sparse_matvec(sr_ctx* ctx, int ring, size_t nrows, size_t ncols, const uint64_t* row_ptr,
+                     const uint64_t* col_idx, const uint64_t* vals, const uint64_t* v, size_t v_limbs, uint64_t* out,
+                     int loc);
+
+/* sr_matmat replaces Matrix<R>::checked_mul_mat / try_mul_mat / Mul<&Matrix<R>> with R = RqNTT
+ * (linear_algebra/src/matrix.rs:148-166, 185-197): out[i][j] = sum_k a[i][k] * m[k][j].  a_rows / m_rows / out_rows
+ * are host arrays of row pointers (rows are separate allocations, matrix.rs:17-21) whose targets live in `loc`.
+ * a_ncols != m_nrows returns SR_ERR_BAD_LENGTH (None / DifferentLengths(self.ncols, m.nrows)). */
+int sr_matmat(sr_ctx* ctx, int ring, const uint64_t* const* a_rows, size_t a_nrows, size_t a_ncols,
+              const uint64_t* const* m_rows, size_t m_nrows, size_t m_ncols, uint64_t* const* out_rows, int loc);
+
+/* sr_ntt_scale_batch replaces MulAssign<&R> for Matrix<R> / SparseMatrix<R> (matrix.rs:207-211,
+ * sparse_matrix.rs:298-302) on one row / on the vals array: every NTT-form element of a_inout *= r (one element). */
+int sr_ntt_scale_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, size_t n_limbs, const uint64_t* r, int loc);
+
 /* ---- per-prime entry points (what each model module binds) --------------------------------- */
 #define SR_DECLARE_RING(tag)                                                                          \
     int sr_##tag##_crt_batch(sr_ctx* ctx, uint64_t* buf, size_t n_limbs, int loc);                   \

@@ -32,6 +32,14 @@ def _bind(path):
     for name in ("sro_gadget_decompose", "sro_gadget_recompose"):
         getattr(L, name).argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_size_t, u64p]
         getattr(L, name).restype = ctypes.c_int
+    L.sro_sparse_matvec.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, u64p, u64p, u64p, u64p,
+                                    ctypes.c_size_t, u64p]
+    L.sro_sparse_matvec.restype = ctypes.c_int
+    L.sro_matmat.argtypes = [ctypes.c_int, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t,
+                             ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(u64p)]
+    L.sro_matmat.restype = ctypes.c_int
+    L.sro_scale.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, u64p]
+    L.sro_scale.restype = None
     L.sro_crt_stages.argtypes = [ctypes.c_int, u64p]
     L.sro_crt_stages.restype = None
     return L
@@ -102,6 +110,37 @@ def matvec(ring, rows, v, threads=1, L=None):
     out = np.zeros(kappa * w, dtype=np.uint64)
     rc = (L or lib()).sro_matvec(RINGS[ring], arr, kappa, m, _p(v), v.size // w, _p(out), threads)
     return None if rc else out
+
+
+def sparse_matvec(ring, nrows, ncols, row_ptr, col_idx, vals, v, L=None):
+    """CSR arrays (uint64) -> nrows*words array; None on length mismatch; IndexError on a bad column index."""
+    w = words(ring)
+    out = np.zeros(nrows * w, dtype=np.uint64)
+    pad = np.zeros(1, dtype=np.uint64)
+    rc = (L or lib()).sro_sparse_matvec(RINGS[ring], nrows, ncols, _p(row_ptr), _p(col_idx if col_idx.size else pad),
+                                        _p(vals if vals.size else pad), _p(v if v.size else pad), v.size // w, _p(out))
+    if rc == 2:
+        raise IndexError("column index out of range")
+    return None if rc else out
+
+
+def matmat(ring, a_rows, m_rows, L=None):
+    """a_rows / m_rows: lists of uint64 row arrays -> list of output rows, or None on a shape mismatch."""
+    w = words(ring)
+    a_ncols = a_rows[0].size // w if a_rows else 0
+    m_ncols = m_rows[0].size // w if m_rows else 0
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    outs = [np.zeros(m_ncols * w, dtype=np.uint64) for _ in a_rows]
+    pad = np.zeros(1, dtype=np.uint64)
+    tab = lambda rows: (u64p * max(len(rows), 1))(*[_p(r if r.size else pad) for r in rows])
+    rc = (L or lib()).sro_matmat(RINGS[ring], tab(a_rows), len(a_rows), a_ncols, tab(m_rows), len(m_rows), m_ncols,
+                                 tab(outs))
+    return None if rc else outs
+
+
+def scale(ring, a, r, L=None):
+    (L or lib()).sro_scale(RINGS[ring], _p(a), a.size // words(ring), _p(r))
+    return a
 
 
 def reduce(ring, polys, coeffs_per_poly, L=None):

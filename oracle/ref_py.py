@@ -362,6 +362,44 @@ def matvec(M, rows, v):
     return out
 
 
+def sparse_matvec(M, ncols, coeffs, v):
+    """sparse_matrix.rs:201-212 with R = RqNTT: coeffs[i] = [(element, column), ...];
+    out[i] = sum of element * v[column], Sum folded from ZERO; None when ncols != len(v)."""
+    if ncols != len(v):
+        return None
+    out = []
+    for row in coeffs:
+        acc = [0] * M.D
+        for r, j in row:
+            acc = ntt_add(M, acc, M.ntt_mul(r, v[j]))  # v[j] out of range: IndexError, the reference panics
+        out.append(acc)
+    return out
+
+
+def matmat(M, a, m):
+    """matrix.rs:148-166 with R = RqNTT: out[i][j] = sum_k a[i][k] * m[k][j]; None when a.ncols != m.nrows
+    (ncols of a matrix = length of its first row, 0 when it has no rows: matrix.rs:100-108)."""
+    a_ncols = len(a[0]) if a else 0
+    m_ncols = len(m[0]) if m else 0
+    if a_ncols != len(m):
+        return None
+    out = []
+    for row in a:
+        orow = []
+        for j in range(m_ncols):
+            acc = [0] * M.D
+            for k in range(a_ncols):
+                acc = ntt_add(M, acc, M.ntt_mul(row[k], m[k][j]))
+            orow.append(acc)
+        out.append(orow)
+    return out
+
+
+def scale(M, elems, r):
+    """MulAssign<&R> on every entry (matrix.rs:207-211, sparse_matrix.rs:298-302)."""
+    return [M.ntt_mul(x, r) for x in elems]
+
+
 def to_raw(M, vals):
     """standard-form ints -> flat list of little-endian u64 limbs of x*R mod p (ark-ff MontBackend)."""
     out = []

@@ -442,6 +442,53 @@ int sro_matvec(int ring, const u64* const* rows, size_t kappa, size_t ncols, con
     return 0;
 }
 
+/* The callers' other linear maps.
+ * Sparse mat-vec (sparse_matrix.rs:201-212) on the CSR image of coeffs: out[i] = sum_e vals[e] * v[col_idx[e]] for
+ * e in [row_ptr[i], row_ptr[i+1]).  Returns 1 when ncols != vlen (None), 2 on a column index >= ncols (panic). */
+int sro_sparse_matvec(int ring, size_t nrows, size_t ncols, const u64* row_ptr, const u64* col_idx, const u64* vals,
+                      const u64* v, size_t vlen, u64* out) {
+    pthread_once(&once, init_all);
+    if (ncols != vlen) return 1;
+    size_t w = sro_elem_words(ring);
+    u64 tmp[72];
+    for (size_t i = 0; i < nrows; i++) {
+        u64* acc = out + i * w;
+        memset(acc, 0, w * 8);
+        for (u64 e = row_ptr[i]; e < row_ptr[i + 1]; e++) {
+            if (col_idx[e] >= ncols) return 2;
+            memcpy(tmp, vals + e * w, w * 8);
+            nttmul1(ring, tmp, v + col_idx[e] * w);
+            nttadd1(ring, acc, tmp);
+        }
+    }
+    return 0;
+}
+/* Dense mat-mat (matrix.rs:148-166): out[i][j] = sum_k a[i][k] * m[k][j]; returns 1 when a_ncols != m_nrows. */
+int sro_matmat(int ring, const u64* const* a_rows, size_t a_nrows, size_t a_ncols, const u64* const* m_rows,
+               size_t m_nrows, size_t m_ncols, u64* const* out_rows) {
+    pthread_once(&once, init_all);
+    if (a_ncols != m_nrows) return 1;
+    size_t w = sro_elem_words(ring);
+    u64 tmp[72];
+    for (size_t i = 0; i < a_nrows; i++)
+        for (size_t j = 0; j < m_ncols; j++) {
+            u64* acc = out_rows[i] + j * w;
+            memset(acc, 0, w * 8);
+            for (size_t k = 0; k < a_ncols; k++) {
+                memcpy(tmp, a_rows[i] + k * w, w * 8);
+                nttmul1(ring, tmp, m_rows[k] + j * w);
+                nttadd1(ring, acc, tmp);
+            }
+        }
+    return 0;
+}
+/* MulAssign<&R> on a batch (matrix.rs:207-211, sparse_matrix.rs:298-302): a[e] *= r */
+void sro_scale(int ring, u64* a, size_t n, const u64* r) {
+    pthread_once(&once, init_all);
+    size_t w = sro_elem_words(ring);
+    for (size_t e = 0; e < n; e++) nttmul1(ring, a + e * w, r);
+}
+
 /* Coefficient-form helpers.  reduce: n polynomials of len field elements (D <= len <= 2D) -> n elements
  * (goldilocks/mod.rs:75-98, babybear/mod.rs:87-110, stark_prime/mod.rs:40-47). */
 void sro_reduce(int ring, const u64* in, size_t n, size_t len, u64* out) {

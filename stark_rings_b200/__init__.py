@@ -11,6 +11,6 @@ from .rings import (  # noqa: F401
     CONFIGS, CRT, ICRT, BabyBearRingConfig, Context, GoldilocksRingConfig, RingConfig, RqNTT, RqPoly,
     StarkRingConfig, default_context,
 )
-from .linalg import Matrix  # noqa: F401
+from .linalg import Matrix, SparseMatrix  # noqa: F401
 
 __version__ = "0.1.0"

@@ -60,6 +60,9 @@ _sig("sr_reduce_batch", _int, _vp, _int, _vp, _sz, _sz, _vp, _int)
 _sig("sr_rot_batch", _int, _vp, _int, _vp, _vp, _sz, _int)
 _sig("sr_gadget_decompose", _int, _vp, _int, _vp, _sz, ctypes.c_uint64, ctypes.c_uint64, _sz, _vp, _int)
 _sig("sr_gadget_recompose", _int, _vp, _int, _vp, _sz, ctypes.c_uint64, ctypes.c_uint64, _sz, _vp, _int)
+_sig("sr_sparse_matvec", _int, _vp, _int, _sz, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _int)
+_sig("sr_matmat", _int, _vp, _int, _pp, _sz, _sz, _pp, _sz, _sz, _pp, _int)
+_sig("sr_ntt_scale_batch", _int, _vp, _int, _vp, _sz, _vp, _int)
 for _tag in ("gl", "bb", "sp"):
     _sig("sr_%s_crt_batch" % _tag, _int, _vp, _vp, _sz, _int)
     _sig("sr_%s_icrt_batch" % _tag, _int, _vp, _vp, _sz, _int)
@@ -73,6 +76,6 @@ EXPORTS = [
     "sr_kernel_launches", "sr_dev_alloc", "sr_dev_free", "sr_host_alloc", "sr_host_free", "sr_h2d", "sr_d2h",
     "sr_timer_start", "sr_timer_stop", "sr_crt_batch", "sr_icrt_batch", "sr_ntt_mul_batch", "sr_ring_mul_batch",
     "sr_matvec", "sr_matvec_partial", "sr_modsum_partials", "sr_reduce_batch", "sr_rot_batch",
-    "sr_gadget_decompose", "sr_gadget_recompose",
+    "sr_gadget_decompose", "sr_gadget_recompose", "sr_sparse_matvec", "sr_matmat", "sr_ntt_scale_batch",
 ] + ["sr_%s_%s" % (t, f) for t in ("gl", "bb", "sp")
      for f in ("crt_batch", "icrt_batch", "ntt_mul_batch", "ring_mul_batch", "matvec")]

@@ -39,10 +39,23 @@ constexpr int root_exp(int k) {
     return t[k];
 }
 
-SR_HD u64 canon(u64 x) { return x >= P ? x - P : x; }
-
 #if defined(__CUDA_ARCH__)
 SR_D u64 mk64(u32 lo, u32 hi) { return (u64)lo | ((u64)hi << 32); }
+// x >= p  <=>  hi == 2^32 - 1 and lo != 0, and then x - p = lo - 1: two predicate tests and two predicated
+// word updates instead of a 64-bit compare, a 64-bit subtraction and two selects
+SR_D u64 canon(u64 x) {
+    u32 lo = (u32)x, hi = (u32)(x >> 32);
+    if (hi == 0xFFFFFFFFu && lo != 0u) {
+        lo -= 1u;
+        hi = 0u;
+    }
+    return mk64(lo, hi);
+}
+#else
+SR_HD u64 canon(u64 x) { return x >= P ? x - P : x; }
+#endif
+
+#if defined(__CUDA_ARCH__)
 // a weak, b canonical -> weak
 SR_D u64 add(u64 a, u64 b) {
     u32 lo, hi;
@@ -169,20 +182,22 @@ SR_HD void bfly(u64 (&c)[D]) {
     }
 }
 // (a, b) <- (a + b, w (a - b)); w = -2^e turns a - b into b - a
-template <int LO, int SPAN, int K>
+// CANON_IN: the inputs are already canonical (skips two canonicalisations per butterfly)
+template <int LO, int SPAN, int K, bool CANON_IN = false>
 SR_HD void ibfly(u64 (&c)[D]) {
     constexpr int E = root_exp(K);
 #pragma unroll
     for (int i = 0; i < SPAN; i++) {
         const u64 a = c[LO + i], b = c[LO + SPAN + i];
-        const u64 ca = canon(a), cb = canon(b);
+        const u64 ca = CANON_IN ? a : canon(a), cb = CANON_IN ? b : canon(b);
         c[LO + i] = add(a, cb);
         c[LO + SPAN + i] = mul_pow2<E % 96>((E >= 96) ? sub(b, ca) : sub(a, cb));
     }
 }
 
 // ntt.rs:146-225.  Input CANONICAL (as stored in memory); output weak.
-SR_HD void crt_stages(u64 (&c)[D]) {
+// first two stages: the four quarters then hold f mod X^6 - r^2, r^14, r^10, r^22
+SR_HD void crt_stages12(u64 (&c)[D]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         // zeta = ROOTS_OF_UNITY_24[4] = 2^160 = -2^64:  z = -z'  with z' = 2^64 b
@@ -193,6 +208,9 @@ SR_HD void crt_stages(u64 (&c)[D]) {
     }
     bfly<0, 6, 2>(c);
     bfly<12, 6, 10>(c);
+}
+SR_HD void crt_stages(u64 (&c)[D]) {
+    crt_stages12(c);
     bfly<0, 3, 1>(c);
     bfly<6, 3, 7>(c);
     bfly<12, 3, 5>(c);
@@ -275,7 +293,7 @@ SR_D void acc_mad(Acc& A, u64 a, u64 b) {
         : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3)
         : "r"(al), "r"(ah), "r"(bl), "r"(bh));
 }
-// canonical residue of the accumulated value (valid while the true sum is < 2^192)
+// canonical residue of the accumulated value; valid while the true sum is < 2^160 (up to 2^32 products)
 SR_D u64 acc_reduce(const Acc& A) {
     u64 c = (u64)A.e1 + A.o1;
     const u32 l0 = A.e0, l1 = (u32)c;
@@ -283,32 +301,30 @@ SR_D u64 acc_reduce(const Acc& A) {
     const u32 l2 = (u32)c;
     c = (c >> 32) + (u64)A.e3 + A.o3;
     const u32 l3 = (u32)c;
-    c = (c >> 32) + (u64)A.e4;
-    const u32 l4 = (u32)c, l5 = (u32)(c >> 32);
-    // 2^128 = -2^32, 2^160 = 1 - 2^32 (mod p); l4 2^32 <= p - 1 and l5, l5 2^32 are canonical
+    const u32 l4 = (u32)(c >> 32) + A.e4;
+    // 2^128 = -2^32 (mod p); l4 2^32 <= p - 1 is canonical
     u64 r = reduce128(mk64(l0, l1), mk64(l2, l3));
     r = sub(r, (u64)l4 << 32);
-    r = add(r, (u64)l5);
-    r = sub(r, (u64)l5 << 32);
     return canon(r);
 }
 #endif
 
 // z = x * y in F_p[u]/(u^3 - 2^RHO_EXP), then times 2^POST_EXP.  Weak in, weak out.
+// Device: y1, y2 are pre-multiplied by rho = 2^RHO_EXP (two shift-reductions), after which every output coefficient
+// is one lazy sum of three 64 x 64 products: 9 accumulations and 3 reductions per slot.
 template <int RHO_EXP, int POST_EXP>
 SR_HD void slot_mul(u64* z, const u64* x, const u64* y) {
     const u64 x0 = x[0], x1 = x[1], x2 = x[2], y0 = y[0], y1 = y[1], y2 = y[2];
     u64 c0, c1, c2;
 #if defined(__CUDA_ARCH__)
-    Acc d0, d1, d2, d3, d4;  // the five diagonals of the 3 x 3 product
-    acc_zero(d0); acc_zero(d1); acc_zero(d2); acc_zero(d3); acc_zero(d4);
-    acc_mad(d0, x0, y0);
-    acc_mad(d1, x0, y1); acc_mad(d1, x1, y0);
+    const u64 r1 = mul_pow2<RHO_EXP>(y1), r2 = mul_pow2<RHO_EXP>(y2);
+    Acc d0, d1, d2;
+    acc_zero(d0); acc_zero(d1); acc_zero(d2);
+    acc_mad(d0, x0, y0); acc_mad(d0, x1, r2); acc_mad(d0, x2, r1);
+    acc_mad(d1, x0, y1); acc_mad(d1, x1, y0); acc_mad(d1, x2, r2);
     acc_mad(d2, x0, y2); acc_mad(d2, x1, y1); acc_mad(d2, x2, y0);
-    acc_mad(d3, x1, y2); acc_mad(d3, x2, y1);
-    acc_mad(d4, x2, y2);
-    c0 = add(mul_pow2<RHO_EXP>(acc_reduce(d3)), acc_reduce(d0));
-    c1 = add(mul_pow2<RHO_EXP>(acc_reduce(d4)), acc_reduce(d1));
+    c0 = acc_reduce(d0);
+    c1 = acc_reduce(d1);
     c2 = acc_reduce(d2);
 #else
     c0 = add(mul(x0, y0), mul_pow2<RHO_EXP>(add(mul(x1, y2), mul(x2, y1))));
@@ -326,7 +342,9 @@ SR_HD void slot_mul(u64* z, const u64* x, const u64* y) {
 // ntt_form.rs:159-175 on raw Montgomery limbs: a <- a * b * 2^-64 slot-wise, 2^-64 = 2^128
 SR_HD void ntt_mul(u64 (&a)[D], const u64 (&b)[D]) {
 #pragma unroll
-    for (int s = 0; s < 8; s++) slot_mul<root_exp(1), 128>(&a[3 * s], &a[3 * s], &b[3 * s]);
+    for (int s = 0; s < 8; s++) {
+        slot_mul<root_exp(1), 128>(&a[3 * s], &a[3 * s], &b[3 * s]);
+    }
 #pragma unroll
     for (int i = 0; i < D; i++) a[i] = canon(a[i]);
 }

@@ -20,7 +20,9 @@ batch_kernel(const u64* a, const u64* b, u64* out, size_t n) {
         stage_in<R, T>(sA, a + e0 * R::WORDS64, ne);
         if (OP == OP_NTT_MUL || OP == OP_RING_MUL) stage_in<R, T>(sB, b + e0 * R::WORDS64, ne);
         __syncthreads();
-        if ((int)threadIdx.x < ne) {
+        // rows >= ne of a ragged last tile hold stale data: transforming them is harmless (straight-line integer
+        // code, never stored) and keeps every thread on the same path, which the phase barriers of gl_ring.cuh need
+        {
             u32* rowA = sA + threadIdx.x * R::ROW;
             u32* rowB = sB + threadIdx.x * R::ROW;
             if (OP == OP_CRT) R::op_crt(rowA);

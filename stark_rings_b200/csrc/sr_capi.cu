@@ -29,6 +29,12 @@ cudaError_t coeff_launch(int ring, int op, const u64* in, u64* out, size_t n, in
 // balanced gadget decomposition / recomposition (sr_decomp.cu): op 0 = decompose, op 1 = recompose
 cudaError_t decomp_launch(int ring, int op, const u64* in, u64* out, size_t n, unsigned long long b, u64 b_std, int pad,
                           int* overflow, cudaStream_t st);
+// sparse mat-vec, dense mat-mat, scalar scaling (sr_sparse.cu)
+cudaError_t sparse_matvec_launch(int ring, const u64* row_ptr, const u64* col_idx, const u64* vals, const u64* v,
+                                 size_t nrows, size_t ncols, size_t nnz, u64* out, int* bad, cudaStream_t st);
+cudaError_t matmat_launch(int ring, const u64* const* a_rows, const u64* const* m_rows, u64* const* out_rows,
+                          size_t a_nrows, size_t inner, size_t m_ncols, cudaStream_t st);
+cudaError_t scale_launch(int ring, u64* a, const u64* r, size_t n, cudaStream_t st);
 }  // namespace sr
 
 using sr::u64;
@@ -253,6 +259,156 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
     CUX(cudaStreamSynchronize(st));
 #undef CUX
     cleanup();
+    return SR_OK;
+}
+
+// Temporary device allocations of one call (host-buffer paths of the linear-algebra entry points)
+struct DevTemps {
+    std::vector<void*> ptrs;
+    ~DevTemps() {
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+    }
+    cudaError_t alloc(void** p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    // device copy of a host array (async on st)
+    cudaError_t upload(void** p, const void* host, size_t bytes, cudaStream_t st) {
+        cudaError_t e = alloc(p, bytes);
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(*p, host, bytes, cudaMemcpyHostToDevice, st);
+        return e;
+    }
+};
+
+int sparse_matvec_impl(sr_ctx* ctx, int ring, size_t nrows, size_t ncols, const u64* row_ptr, const u64* col_idx,
+                       const u64* vals, const u64* v, size_t v_limbs, u64* out, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (v_limbs % w != 0 || v_limbs / w != ncols)
+        return fail(ctx, SR_ERR_BAD_LENGTH,
+                    "DifferentLengths(" + std::to_string(ncols) + ", " + std::to_string(v_limbs / w) + ")");
+    if (nrows == 0) return SR_OK;
+    if (!row_ptr || !out) return fail(ctx, SR_ERR_INVALID, "null buffer");
+    if (loc != SR_DEVICE && loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
+    // nnz = row_ptr[nrows]
+    u64 ends[2] = {0, 0};
+    if (loc == SR_DEVICE) {
+        CU(cudaMemcpyAsync(&ends[0], row_ptr, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(&ends[1], row_ptr + nrows, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    } else {
+        ends[0] = row_ptr[0];
+        ends[1] = row_ptr[nrows];
+    }
+    if (ends[0] != 0) return fail(ctx, SR_ERR_INVALID, "row_ptr[0] must be 0");
+    const size_t nnz = (size_t)ends[1];
+    if (nnz && (!col_idx || !vals || !v)) return fail(ctx, SR_ERR_INVALID, "null buffer");
+    DevTemps tmp;
+    int* dbad = nullptr;
+    CU(tmp.alloc((void**)&dbad, sizeof(int)));
+    CU(cudaMemsetAsync(dbad, 0, sizeof(int), st));
+    const u64 *k_rp = row_ptr, *k_ci = col_idx, *k_vals = vals, *k_v = v;
+    u64* k_out = out;
+    if (loc == SR_HOST) {
+        for (size_t i = 0; i < nrows; i++)
+            if (row_ptr[i] > row_ptr[i + 1]) return fail(ctx, SR_ERR_INVALID, "row_ptr must be non-decreasing");
+        CU(tmp.upload((void**)&k_rp, row_ptr, (nrows + 1) * 8, st));
+        CU(tmp.upload((void**)&k_ci, col_idx, nnz * 8, st));
+        CU(tmp.upload((void**)&k_vals, vals, nnz * w * 8, st));
+        CU(tmp.upload((void**)&k_v, v, ncols * w * 8, st));
+        CU(tmp.alloc((void**)&k_out, nrows * w * 8));
+    } else if (!aligned16(vals) || !aligned16(v) || !aligned16(out)) {
+        return fail(ctx, SR_ERR_INVALID, "device buffers must be 16-byte aligned");
+    }
+    CU(sr::sparse_matvec_launch(ring, k_rp, k_ci, k_vals, k_v, nrows, ncols, nnz, k_out, dbad, st));
+    ctx->launches++;
+    if (loc == SR_HOST) CU(cudaMemcpyAsync(out, k_out, nrows * w * 8, cudaMemcpyDeviceToHost, st));
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (bad) return fail(ctx, SR_ERR_INVALID, "column index out of range (the reference panics on v[i])");
+    return SR_OK;
+}
+
+int matmat_impl(sr_ctx* ctx, int ring, const u64* const* a_rows, size_t a_nrows, size_t a_ncols,
+                const u64* const* m_rows, size_t m_nrows, size_t m_ncols, u64* const* out_rows, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (a_ncols != m_nrows)
+        return fail(ctx, SR_ERR_BAD_LENGTH,
+                    "DifferentLengths(" + std::to_string(a_ncols) + ", " + std::to_string(m_nrows) + ")");
+    if (a_nrows == 0 || m_ncols == 0) return SR_OK;
+    if (!a_rows || !out_rows || (m_nrows && !m_rows)) return fail(ctx, SR_ERR_INVALID, "null row table");
+    if (loc != SR_DEVICE && loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    for (size_t i = 0; i < a_nrows; i++)
+        if ((a_ncols && !a_rows[i]) || !out_rows[i]) return fail(ctx, SR_ERR_INVALID, "null row pointer");
+    for (size_t k = 0; k < m_nrows; k++)
+        if (!m_rows[k]) return fail(ctx, SR_ERR_INVALID, "null row pointer");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
+    DevTemps tmp;
+    std::vector<const u64*> ha(a_rows, a_rows + a_nrows), hm(m_rows, m_rows + m_nrows);
+    std::vector<u64*> ho(out_rows, out_rows + a_nrows);
+    if (loc == SR_HOST) {
+        for (size_t i = 0; i < a_nrows; i++) {
+            CU(tmp.upload((void**)&ha[i], a_rows[i], a_ncols * w * 8, st));
+            CU(tmp.alloc((void**)&ho[i], m_ncols * w * 8));
+        }
+        for (size_t k = 0; k < m_nrows; k++) CU(tmp.upload((void**)&hm[k], m_rows[k], m_ncols * w * 8, st));
+    } else {
+        for (size_t i = 0; i < a_nrows; i++)
+            if (!aligned16(ha[i]) || !aligned16(ho[i])) return fail(ctx, SR_ERR_INVALID, "row pointer misaligned");
+        for (size_t k = 0; k < m_nrows; k++)
+            if (!aligned16(hm[k])) return fail(ctx, SR_ERR_INVALID, "row pointer misaligned");
+    }
+    void *da = nullptr, *dm = nullptr, *dout = nullptr;
+    CU(tmp.upload(&da, ha.data(), a_nrows * sizeof(void*), st));
+    CU(tmp.upload(&dm, hm.data(), m_nrows * sizeof(void*), st));
+    CU(tmp.upload(&dout, ho.data(), a_nrows * sizeof(void*), st));
+    CU(sr::matmat_launch(ring, (const u64* const*)da, (const u64* const*)dm, (u64* const*)dout, a_nrows, a_ncols,
+                         m_ncols, st));
+    ctx->launches += (a_nrows + 65534) / 65535;
+    if (loc == SR_HOST)
+        for (size_t i = 0; i < a_nrows; i++)
+            CU(cudaMemcpyAsync(out_rows[i], ho[i], m_ncols * w * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // the pointer tables are temporaries of this call
+    return SR_OK;
+}
+
+int scale_impl(sr_ctx* ctx, int ring, u64* a, size_t n_limbs, const u64* r, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (n_limbs % w != 0) return fail(ctx, SR_ERR_BAD_LENGTH, "slice length is not a whole number of elements");
+    const size_t n = n_limbs / w;
+    if (n == 0) return SR_OK;
+    if (!a || !r) return fail(ctx, SR_ERR_INVALID, "null buffer");
+    CU(cudaSetDevice(ctx->device));
+    if (loc == SR_DEVICE) {
+        if (!aligned16(a) || !aligned16(r)) return fail(ctx, SR_ERR_INVALID, "device buffers must be 16-byte aligned");
+        CU(sr::scale_launch(ring, a, r, n, ctx->stream));
+        ctx->launches++;
+        return SR_OK;
+    }
+    if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    cudaStream_t st = ctx->own_stream;
+    DevTemps tmp;
+    u64 *da = nullptr, *dr = nullptr;
+    CU(tmp.upload((void**)&da, a, n_limbs * 8, st));
+    CU(tmp.upload((void**)&dr, r, w * 8, st));
+    CU(sr::scale_launch(ring, da, dr, n, st));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(a, da, n_limbs * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SR_OK;
 }
 
@@ -565,6 +721,19 @@ int sr_gadget_decompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limb
 int sr_gadget_recompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint64_t b_lo, uint64_t b_hi,
                         size_t padding_size, uint64_t* out, int loc) {
     return decomp_impl(ctx, ring, 1, in, n_limbs, b_lo, b_hi, padding_size, out, loc);
+}
+
+int sr_sparse_matvec(sr_ctx* ctx, int ring, size_t nrows, size_t ncols, const uint64_t* row_ptr,
+                     const uint64_t* col_idx, const uint64_t* vals, const uint64_t* v, size_t v_limbs, uint64_t* out,
+                     int loc) {
+    return sparse_matvec_impl(ctx, ring, nrows, ncols, row_ptr, col_idx, vals, v, v_limbs, out, loc);
+}
+int sr_matmat(sr_ctx* ctx, int ring, const uint64_t* const* a_rows, size_t a_nrows, size_t a_ncols,
+              const uint64_t* const* m_rows, size_t m_nrows, size_t m_ncols, uint64_t* const* out_rows, int loc) {
+    return matmat_impl(ctx, ring, a_rows, a_nrows, a_ncols, m_rows, m_nrows, m_ncols, out_rows, loc);
+}
+int sr_ntt_scale_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, size_t n_limbs, const uint64_t* r, int loc) {
+    return scale_impl(ctx, ring, a_inout, n_limbs, r, loc);
 }
 
 #define SR_DEFINE_RING(tag, RING)                                                                             \

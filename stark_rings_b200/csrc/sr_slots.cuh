@@ -1,0 +1,95 @@
+// Per-ring CRT-slot traits shared by the mat-vec kernels (sr_matvec.cu) and the sparse / matrix-matrix kernels
+// (sr_sparse.cu): one Val = one slot of an NTT-form element (Fq3 / Fq9 / Fq), with the slot product of
+// ntt_form.rs:159-175 on raw Montgomery limbs and the slot addition of ntt_form.rs:588-601.
+#pragma once
+#include "bb_ring.cuh"
+#include "gl_ring.cuh"
+#include "sp_ring.cuh"
+
+namespace sr {
+
+struct GLSlot {
+    static constexpr int SLOTS = 8, SLOT_U64 = 3, ELEM_U64 = 24;
+    struct Val { u64 c[3]; };
+    SR_D static Val load(const u64* p) { Val v; v.c[0] = __ldcs(p); v.c[1] = __ldcs(p + 1); v.c[2] = __ldcs(p + 2); return v; }
+    SR_D static Val load_cached(const u64* p) { Val v; v.c[0] = p[0]; v.c[1] = p[1]; v.c[2] = p[2]; return v; }
+    SR_D static void store(u64* p, const Val& v) { p[0] = v.c[0]; p[1] = v.c[1]; p[2] = v.c[2]; }
+    SR_D static Val zero() { Val v; v.c[0] = v.c[1] = v.c[2] = 0; return v; }
+    // gl:: arithmetic is weak-form (gl_ring.cuh); values stored in Val are kept canonical
+    SR_D static Val mul(const Val& a, const Val& b) {
+        Val z;
+        gl::slot_mul<gl::root_exp(1), 128>(z.c, a.c, b.c);
+#pragma unroll
+        for (int i = 0; i < 3; i++) z.c[i] = gl::canon(z.c[i]);
+        return z;
+    }
+    SR_D static void acc(Val& s, const Val& x) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) s.c[i] = gl::canon(gl::add(s.c[i], x.c[i]));
+    }
+};
+struct BBSlot {
+    static constexpr int SLOTS = 8, SLOT_U64 = 9, ELEM_U64 = 72;
+    struct Val { u32 c[9]; };
+    SR_D static Val load(const u64* p) {
+        Val v;
+        const u32* q = reinterpret_cast<const u32*>(p);
+#pragma unroll
+        for (int i = 0; i < 9; i++) v.c[i] = __ldcs(q + 2 * i);
+        return v;
+    }
+    SR_D static Val load_cached(const u64* p) {
+        Val v;
+        const u32* q = reinterpret_cast<const u32*>(p);
+#pragma unroll
+        for (int i = 0; i < 9; i++) v.c[i] = q[2 * i];
+        return v;
+    }
+    SR_D static void store(u64* p, const Val& v) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) p[i] = v.c[i];
+    }
+    SR_D static Val zero() {
+        Val v;
+#pragma unroll
+        for (int i = 0; i < 9; i++) v.c[i] = 0;
+        return v;
+    }
+    SR_D static Val mul(const Val& a, const Val& b) { Val z; bb::slot_mul_ntt(z.c, a.c, b.c); return z; }
+    SR_D static void acc(Val& s, const Val& x) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) s.c[i] = bb::add(s.c[i], x.c[i]);
+    }
+};
+struct SPSlot {
+    static constexpr int SLOTS = 16, SLOT_U64 = 4, ELEM_U64 = 64;
+    typedef sp::Fe Val;
+    SR_D static Val load(const u64* p) {
+        Val v;
+        uint4 lo = __ldcs(reinterpret_cast<const uint4*>(p)), hi = __ldcs(reinterpret_cast<const uint4*>(p) + 1);
+        v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w;
+        v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+        return v;
+    }
+    SR_D static Val load_cached(const u64* p) {
+        Val v;
+        uint4 lo = reinterpret_cast<const uint4*>(p)[0], hi = reinterpret_cast<const uint4*>(p)[1];
+        v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w;
+        v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+        return v;
+    }
+    SR_D static void store(u64* p, const Val& v) {
+        reinterpret_cast<uint4*>(p)[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+        reinterpret_cast<uint4*>(p)[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    }
+    SR_D static Val zero() {
+        Val v;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v.v[i] = 0;
+        return v;
+    }
+    SR_D static Val mul(const Val& a, const Val& b) { Val z; sp::mont_mul(z, a, b); return z; }
+    SR_D static void acc(Val& s, const Val& x) { Val t; sp::add(t, s, x); s = t; }
+};
+
+}  // namespace sr

@@ -7,6 +7,7 @@
 #include "bb_half.cuh"
 #include "bb_ring.cuh"
 #include "gl_ring.cuh"
+#include "gl_fused6.cuh"
 #include "sp_half.cuh"
 #include "sp_ring.cuh"
 
@@ -72,6 +73,14 @@ void hc_gl_ring_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
     u64 x[24], y[24]; memcpy(x, a, 192); memcpy(y, b, 192);
     gl::crt_stages(x); gl::crt_stages(y); gl::fused_mul_icrt(y, x); memcpy(out, y, 192);
 }
+
+// degree-6 formulation (gl_fused6.cuh) used by the fused kernel
+void hc_gl_ring_mul_fused6(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    u64 rows[48]; memcpy(rows, a, 192); memcpy(rows + 24, b, 192);
+    gl::ring_mul_fused6(rows, rows + 24, 2); memcpy(out, rows, 192);
+}
+void hc_gl_ntt_mul_rolled(uint64_t* a, const uint64_t* b) { gl::ntt_mul_rolled(a, b); }
+uint64_t hc_gl_mul_pow2_rt(uint64_t x, int e) { return gl::canon(gl::mul_pow2_rt(x, e)); }
 
 void hc_sp_crt(uint64_t* e) { sp::Fe c[16]; memcpy(c, e, 512); sp::crt(c); memcpy(e, c, 512); }
 void hc_sp_icrt(uint64_t* e) { sp::Fe c[16]; memcpy(c, e, 512); sp::icrt(c); memcpy(e, c, 512); }

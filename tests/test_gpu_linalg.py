@@ -1,0 +1,149 @@
+"""GPU parity for SURVEY 8f-3 (sparse mat-vec, dense mat-mat, scalar scaling over RqNTT): the CUDA path through the
+C ABI against the C oracle on identical seeded inputs, plus the reference's own known-answer matrices
+(linear_algebra/src/sparse_matrix.rs:305-377, matrix.rs:232-262) embedded as constant ring elements.  Bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as C
+from oracle import ref_py as O
+from tests.util import WORDS, rand_raw
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["goldilocks", "babybear", "stark_prime"]
+
+
+@pytest.fixture(scope="module")
+def S():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import stark_rings_b200 as S
+    S.default_context(0)
+    return S
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(a.view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def rand_csr(name, nrows, ncols, max_nnz, seed):
+    rng = np.random.default_rng(seed)
+    counts = rng.integers(0, max_nnz + 1, size=nrows)
+    counts[rng.integers(0, nrows)] = 0  # an empty row -> ZERO
+    row_ptr = np.zeros(nrows + 1, dtype=np.uint64)
+    row_ptr[1:] = np.cumsum(counts)
+    nnz = int(row_ptr[-1])
+    col_idx = rng.integers(0, ncols, size=nnz).astype(np.uint64)  # repeats inside a row are legal
+    vals = rand_raw(name, nnz, seed + 1, edge=nnz >= 2) if nnz else np.empty(0, dtype=np.uint64)
+    return row_ptr, col_idx, vals
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("nrows,ncols,max_nnz", [(1, 1, 1), (7, 5, 3), (300, 129, 6), (40, 2000, 64), (5, 4000, 3000)])
+def test_sparse_matvec(S, name, nrows, ncols, max_nnz):
+    cfg = S.CONFIGS[name]
+    rp, ci, vals = rand_csr(name, nrows, ncols, max_nnz, 7 * nrows + ncols)
+    v = rand_raw(name, ncols, 11 + ncols)
+    want = C.sparse_matvec(name, nrows, ncols, rp, ci, vals, v)
+    A = S.SparseMatrix(nrows, ncols, dev(rp), dev(ci), S.RqNTT(cfg, dev(vals)))
+    y = A.try_mul_vec(S.RqNTT(cfg, dev(v)))
+    assert np.array_equal(host(y.data), want)
+    Ah = S.SparseMatrix(nrows, ncols, rp, ci, S.RqNTT(cfg, vals))
+    yh = Ah @ S.RqNTT(cfg, v)
+    assert np.array_equal(yh.data, want)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_sparse_reference_kat_and_errors(S, name):
+    """sparse_matrix.rs:340-351: sample_sparse * [1, 2, 3] = [4, 0, 18]; a 2-vector is Err(DifferentLengths)."""
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    const = lambda c: np.array(O.to_raw(M, M.crt([c] + [0] * (M.D - 1))), dtype=np.uint64)
+    coeffs = [[(const(2), 1)], [], [(const(1), 0), (const(4), 1), (const(3), 2)]]
+    v = np.concatenate([const(1), const(2), const(3)])
+    want = np.concatenate([const(4), const(0), const(18)])
+    for device in (None, "cuda"):
+        A = S.SparseMatrix.from_coeffs(cfg, 3, 3, coeffs, device=device)
+        vv = S.RqNTT(cfg, dev(v) if device else v)
+        got = A.try_mul_vec(vv).data
+        assert np.array_equal(host(got) if device else got, want)
+        bad = S.RqNTT(cfg, dev(v[: 2 * cfg.limbs].copy()) if device else v[: 2 * cfg.limbs].copy())
+        assert A.checked_mul_vec(bad) is None
+        with pytest.raises(S.DifferentLengths) as ei:
+            A.try_mul_vec(bad)
+        assert ei.value.lengths == (3, 2)
+        # identity (sparse_matrix.rs:319-327)
+        I = S.SparseMatrix.identity(cfg, 3, const(1), device=device)
+        got = (I @ vv).data
+        assert np.array_equal(host(got) if device else got, v)
+        # *= 3 (sparse_matrix.rs:353-364): [[0, 6, 0], [0, 0, 0], [3, 12, 9]]
+        three = S.RqNTT(cfg, dev(const(3)) if device else const(3))
+        A *= three
+        ones = np.concatenate([const(1)] * 3)
+        got = (A @ S.RqNTT(cfg, dev(ones) if device else ones)).data
+        assert np.array_equal(host(got) if device else got, np.concatenate([const(6), const(0), const(24)]))
+        assert [j for row in A.to_coeffs() for _, j in row] == [1, 0, 1, 2]
+    # a column index past ncols: the reference panics on v[*i]
+    A = S.SparseMatrix(1, 2, dev(np.array([0, 1], dtype=np.uint64)), dev(np.array([2], dtype=np.uint64)),
+                       S.RqNTT(cfg, dev(const(1))))
+    with pytest.raises(S.StarkRingsError):
+        A.try_mul_vec(S.RqNTT(cfg, dev(v[: 2 * cfg.limbs].copy())))
+    # no rows / no entries
+    E = S.SparseMatrix.from_coeffs(cfg, 2, 3, [[], []], device="cuda")
+    assert not host((E @ S.RqNTT(cfg, dev(v))).data).any()
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 4, 5), (2, 33, 130), (70, 3, 2)])
+def test_matmat(S, name, shape):
+    cfg = S.CONFIGS[name]
+    n, k, m = shape
+    a = [rand_raw(name, k, 100 + i + n) for i in range(n)]
+    b = [rand_raw(name, m, 200 + i + k) for i in range(k)]
+    want = C.matmat(name, a, b)
+    A = S.Matrix([S.RqNTT(cfg, dev(r)) for r in a])
+    B = S.Matrix([S.RqNTT(cfg, dev(r)) for r in b])
+    P = A.try_mul_mat(B)
+    assert P.nrows == n and P.ncols == m
+    assert all(np.array_equal(host(r.data), w) for r, w in zip(P.vals, want))
+    Ph = S.Matrix([S.RqNTT(cfg, r) for r in a]).try_mul_mat(S.Matrix([S.RqNTT(cfg, r) for r in b]))
+    assert all(np.array_equal(r.data, w) for r, w in zip(Ph.vals, want))
+    # (A B) v == A (B v) on the device
+    v = S.RqNTT(cfg, dev(rand_raw(name, m, 5)))
+    assert np.array_equal(host((P @ v).data), host((A @ (B @ v)).data))
+    # shape mismatch (matrix.rs:259-261)
+    assert B.checked_mul_mat(B) is None if k != m else True
+    if k != m:
+        with pytest.raises(S.DifferentLengths):
+            B.try_mul_mat(B)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_matmat_reference_kat_and_scale(S, name):
+    """matrix.rs:254-262 and 245-252 over constant ring elements."""
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    const = lambda c: np.array(O.to_raw(M, M.crt([c] + [0] * (M.D - 1))), dtype=np.uint64)
+    mat = lambda rows: S.Matrix([S.RqNTT(cfg, dev(np.concatenate([const(c) for c in r]))) for r in rows])
+    m1 = mat([[0, 2, 0], [0, 0, 0], [1, 4, 3]])
+    got = m1.try_mul_mat(mat([[1, 2], [3, 4], [5, 6]]))
+    want = [[6, 8], [0, 0], [28, 36]]
+    for r, w in zip(got.vals, want):
+        assert np.array_equal(host(r.data), np.concatenate([const(c) for c in w]))
+    with pytest.raises(S.DifferentLengths):
+        m1.try_mul_mat(mat([[1, 2], [3, 4]]))
+    m1 *= S.RqNTT(cfg, dev(const(3)))
+    for r, w in zip(m1.vals, [[0, 6, 0], [0, 0, 0], [3, 12, 9]]):
+        assert np.array_equal(host(r.data), np.concatenate([const(c) for c in w]))
+    # random scaling against the oracle, device and host buffers
+    a, r = rand_raw(name, 257, 3), rand_raw(name, 1, 4, edge=False)
+    want = C.scale(name, a.copy(), r)
+    row = S.Matrix([S.RqNTT(cfg, dev(a))])
+    row *= S.RqNTT(cfg, dev(r))
+    assert np.array_equal(host(row.vals[0].data), want)
+    rowh = S.Matrix([S.RqNTT(cfg, a.copy())])
+    rowh *= S.RqNTT(cfg, r)
+    assert np.array_equal(rowh.vals[0].data, want)
