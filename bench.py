@@ -252,6 +252,8 @@ def main():
     ap.add_argument("--e2e-log2n", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--commit-path", default="peer", choices=["peer", "nccl"],
+                    help="commit workload, N > 1: how the per-rank partials reach rank 0")
     ap.add_argument("--graph", action="store_true", help="commit workload, 1 GPU: capture the step in a CUDA graph")
     args = ap.parse_args()
     if args.ring is None:
@@ -323,7 +325,19 @@ def main():
         import ctypes
         from stark_rings_b200 import _lib as L
 
+        peer = None
+        if dist is not None and args.commit_path == "peer":
+            # partials go straight into rank 0's HBM over NVLink from the kernel that produces them; rank 0's
+            # reduction kernel acquires the per-rank flags (stark_rings_b200/dist.py PeerCommit)
+            from stark_rings_b200.dist import PeerCommit
+            peer = PeerCommit(cfg, args.kappa, world, rank, ctx, device_epochs=args.graph)
+        config["exchange"] = "none (1 GPU)" if dist is None else (
+            "NVLink peer-memory mailbox fused into the producing / reducing kernels" if peer else
+            "NCCL all_gather of raw limbs + rank-0 modular sum")
+
         def step():
+            if peer is not None:
+                return peer.commit(A, v, out=result)
             part = A.partial_mul_vec(v)
             if dist is not None:
                 dist.all_gather_into_tensor(gathered, part.data)  # raw limbs; an NCCL sum cannot reduce mod p
@@ -342,10 +356,10 @@ def main():
         step()
     barrier()
     launches_per_step = None
-    if args.workload == "commit" and args.graph and world == 1:
-        # optional, single GPU only: capture the step's kernels in a CUDA graph (the row table is already
-        # resident, see sr_capi.cu).  Measured gain 1% at kappa = 4, m = 2^20; with NCCL in the step the capture
-        # hung in round 1, so multi-GPU runs always use eager launches.
+    if args.workload == "commit" and args.graph and (world == 1 or peer is not None):
+        # optional: capture the step's kernels in a CUDA graph (the row table is already resident, see sr_capi.cu).
+        # 1 GPU: gain 1% at kappa = 4, m = 2^20.  N GPUs: only the peer-memory path can be captured (device-resident
+        # epochs, no collective call in the step); with NCCL in the step the capture hung in round 1.
         try:
             l0 = ctx.kernel_launches
             step()

@@ -110,6 +110,34 @@ int sr_matvec_partial(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t
 int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t nranks, size_t nrows,
                        uint64_t* out, int loc);
 
+/* ---- column-sharded commitment over NVLink peer memory -----------------------------------------
+ * One process per GPU.  The ROOT rank creates a mailbox (device memory) and exports its CUDA IPC handle
+ * (SR_IPC_HANDLE_BYTES bytes), which the caller ships to the other ranks out of band (MPI, torch.distributed
+ * all_gather_object, a pipe ...); they map it with sr_mailbox_open.  Per commitment (epoch = 1, 2, 3 ... the same on
+ * every rank):
+ *   every rank:  sr_commit_send    its share of the columns -> nrows partial elements, written by the LAST KERNEL of
+ *                                  the product straight into the root's mailbox over NVLink, followed by a
+ *                                  release-flag; no NCCL call, no host synchronisation, no extra kernel launch
+ *   root only:   sr_commit_reduce  one kernel that acquires the flags of all ranks and adds the partials mod p
+ *                                  (an NCCL sum cannot reduce mod p) into `out` (device memory of the root)
+ * epoch = 0 selects device-resident epochs: each rank's kernels count their own commitments, so a step issues
+ * identical launches every time and can be captured in a CUDA graph (every rank must then call sr_commit_send
+ * exactly once per commitment, the root sr_commit_reduce once).  Do not mix the two modes on one mailbox.
+ * Both calls are asynchronous on the context's stream.  A wait that exceeds 4 s (a lost peer) sets an error flag,
+ * readable with sr_mailbox_error, instead of hanging the GPU.  The reference has no counterpart (single process);
+ * single-GPU semantics are those of Matrix::checked_mul_vec (matrix.rs:168-178). */
+typedef struct sr_mailbox sr_mailbox;
+#define SR_IPC_HANDLE_BYTES 64
+int sr_mailbox_create(sr_ctx* ctx, int ring, size_t nrows_max, int nranks, sr_mailbox** out,
+                      unsigned char* handle_out /* SR_IPC_HANDLE_BYTES, may be NULL */);
+int sr_mailbox_open(sr_ctx* ctx, int ring, size_t nrows_max, int nranks, const unsigned char* handle,
+                    sr_mailbox** out);
+int sr_mailbox_destroy(sr_ctx* ctx, sr_mailbox* box);
+int sr_mailbox_error(sr_ctx* ctx, sr_mailbox* box, int* timed_out); /* synchronises the context's stream */
+int sr_commit_send(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v,
+                   size_t v_limbs, sr_mailbox* root_box, int rank, uint64_t epoch);
+int sr_commit_reduce(sr_ctx* ctx, int ring, sr_mailbox* own_box, size_t nrows, uint64_t epoch, uint64_t* out);
+
 /* ---- coefficient-form helpers next to the hot path (out of place, out != in) ----
  * sr_reduce_batch replaces CyclotomicConfig::reduce_in_place (goldilocks/mod.rs:75-98, babybear/mod.rs:87-110,
  * stark_prime/mod.rs:40-47) on a batch: `in` holds polynomials of coeffs_per_poly field elements each

@@ -63,6 +63,13 @@ _sig("sr_gadget_recompose", _int, _vp, _int, _vp, _sz, ctypes.c_uint64, ctypes.c
 _sig("sr_sparse_matvec", _int, _vp, _int, _sz, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _int)
 _sig("sr_matmat", _int, _vp, _int, _pp, _sz, _sz, _pp, _sz, _sz, _pp, _int)
 _sig("sr_ntt_scale_batch", _int, _vp, _int, _vp, _sz, _vp, _int)
+_sig("sr_mailbox_create", _int, _vp, _int, _sz, _int, _pp, ctypes.c_char_p)
+_sig("sr_mailbox_open", _int, _vp, _int, _sz, _int, ctypes.c_char_p, _pp)
+_sig("sr_mailbox_destroy", _int, _vp, _vp)
+_sig("sr_mailbox_error", _int, _vp, _vp, ctypes.POINTER(ctypes.c_int))
+_sig("sr_commit_send", _int, _vp, _int, _pp, _sz, _sz, _vp, _sz, _vp, _int, ctypes.c_uint64)
+_sig("sr_commit_reduce", _int, _vp, _int, _vp, _sz, ctypes.c_uint64, _vp)
+SR_IPC_HANDLE_BYTES = 64
 for _tag in ("gl", "bb", "sp"):
     _sig("sr_%s_crt_batch" % _tag, _int, _vp, _vp, _sz, _int)
     _sig("sr_%s_icrt_batch" % _tag, _int, _vp, _vp, _sz, _int)
@@ -77,5 +84,6 @@ EXPORTS = [
     "sr_timer_start", "sr_timer_stop", "sr_crt_batch", "sr_icrt_batch", "sr_ntt_mul_batch", "sr_ring_mul_batch",
     "sr_matvec", "sr_matvec_partial", "sr_modsum_partials", "sr_reduce_batch", "sr_rot_batch",
     "sr_gadget_decompose", "sr_gadget_recompose", "sr_sparse_matvec", "sr_matmat", "sr_ntt_scale_batch",
+    "sr_mailbox_create", "sr_mailbox_open", "sr_mailbox_destroy", "sr_mailbox_error", "sr_commit_send", "sr_commit_reduce",
 ] + ["sr_%s_%s" % (t, f) for t in ("gl", "bb", "sp")
      for f in ("crt_batch", "icrt_batch", "ntt_mul_batch", "ring_mul_batch", "matvec")]

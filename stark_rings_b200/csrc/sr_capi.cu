@@ -21,9 +21,9 @@ cudaError_t sp_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cu
 // scratch (>= matvec_scratch_bytes).  Returns the number of kernels launched via *launches.
 size_t matvec_scratch_bytes(int ring, size_t nrows, int sms);
 cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
-                          u64* out, void* scratch, cudaStream_t st, int sms, int* launches);
-cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t nrows, u64* out,
-                          cudaStream_t st);
+                          u64* out, void* scratch, cudaStream_t st, int sms, int* launches, const PeerSync* ps);
+cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t stride_rows, size_t nrows, u64* out,
+                          cudaStream_t st, const PeerSync* ps);
 // coefficient-form helpers (sr_coeff.cu): op 0 = reduce, op 1 = rot
 cudaError_t coeff_launch(int ring, int op, const u64* in, u64* out, size_t n, int len, cudaStream_t st);
 // balanced gadget decomposition / recomposition (sr_decomp.cu): op 0 = decompose, op 1 = recompose
@@ -60,6 +60,26 @@ struct sr_ctx {
     void* mv_rows = nullptr;  // device copy of the row-pointer table
     size_t mv_rows_cap = 0;
     std::vector<const void*> mv_rows_cached;  // host copy of what mv_rows holds (skip re-upload if unchanged)
+    unsigned* commit_counters = nullptr;      // [2] block-arrival counters of the mailbox kernels (send, reduce)
+};
+
+// Mailbox of the column-sharded commitment: device memory of ONE rank (the root) that every rank maps
+// through CUDA IPC.  Layout: header { flags[MAX_RANKS], consumed, err } in the first 4 KiB, then
+// MAILBOX_DEPTH x nranks x nrows_max partial elements.
+struct sr_mailbox {
+    static constexpr int MAX_RANKS = 64;
+    static constexpr size_t HEADER = 4096;
+    int ring = 0;
+    size_t nrows_max = 0;
+    int nranks = 0;
+    bool owner = false;  // created here (cudaMalloc) or opened from a peer's IPC handle
+    void* base = nullptr;
+    size_t bytes = 0;
+    u64* sent = nullptr;  // device-LOCAL count of the epochs this process has delivered into this mailbox
+    u64* flags() const { return reinterpret_cast<u64*>(base); }
+    u64* consumed() const { return reinterpret_cast<u64*>(base) + MAX_RANKS; }
+    int* err() const { return reinterpret_cast<int*>(reinterpret_cast<u64*>(base) + MAX_RANKS + 1); }
+    u64* slots() const { return reinterpret_cast<u64*>(reinterpret_cast<char*>(base) + HEADER); }
 };
 
 namespace {
@@ -169,7 +189,7 @@ int batch(sr_ctx* ctx, int ring, int op, const u64* a, const u64* b, u64* out, s
 }
 
 int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, size_t ncols, const u64* v,
-                size_t v_limbs, u64* out, int loc) {
+                size_t v_limbs, u64* out, int loc, const sr::PeerSync* ps = nullptr) {
     if (!ctx) return SR_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t w = elem_limbs(ring);
@@ -213,11 +233,11 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
             CU(cudaStreamSynchronize(st));
         }
         CU(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, v, out, ctx->mv_scratch, st,
-                             ctx->sms, &launches));
+                             ctx->sms, &launches, ps));
         ctx->launches += launches;
         return SR_OK;
     }
-    if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    if (loc != SR_HOST || ps) return fail(ctx, SR_ERR_INVALID, "unknown loc");
     // Host path: whole operands are copied to the device (a commitment matrix is normally kept
     // resident with SR_DEVICE; this path exists for drop-in completeness).
     const size_t row_bytes = ncols * w * 8;
@@ -253,7 +273,7 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
     ctx->mv_rows_cached.clear();
     CUX(cudaMemcpyAsync(ctx->mv_rows, drows.data(), nrows * sizeof(void*), cudaMemcpyHostToDevice, st));
     CUX(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, (const u64*)dv, (u64*)dout,
-                          ctx->mv_scratch, st, ctx->sms, &launches));
+                          ctx->mv_scratch, st, ctx->sms, &launches, nullptr));
     ctx->launches += launches;
     CUX(cudaMemcpyAsync(out, dout, nrows * w * 8, cudaMemcpyDeviceToHost, st));
     CUX(cudaStreamSynchronize(st));
@@ -598,7 +618,7 @@ int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t n
     if (!gathered || !out || nranks == 0) return fail(ctx, SR_ERR_INVALID, "null buffer / zero ranks");
     CU(cudaSetDevice(ctx->device));
     if (loc == SR_DEVICE) {
-        CU(sr::modsum_launch(ring, gathered, nranks, nrows, out, ctx->stream));
+        CU(sr::modsum_launch(ring, gathered, nranks, nrows, nrows, out, ctx->stream, nullptr));
         ctx->launches++;
         return SR_OK;
     }
@@ -608,7 +628,8 @@ int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t n
     cudaError_t e = cudaMalloc(&dg, gbytes);
     if (e == cudaSuccess) e = cudaMalloc(&dout, obytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dg, gathered, gbytes, cudaMemcpyHostToDevice, ctx->own_stream);
-    if (e == cudaSuccess) e = sr::modsum_launch(ring, (const u64*)dg, nranks, nrows, (u64*)dout, ctx->own_stream);
+    if (e == cudaSuccess)
+        e = sr::modsum_launch(ring, (const u64*)dg, nranks, nrows, nrows, (u64*)dout, ctx->own_stream, nullptr);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, ctx->own_stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);
     if (dg) cudaFree(dg);
@@ -734,6 +755,148 @@ int sr_matmat(sr_ctx* ctx, int ring, const uint64_t* const* a_rows, size_t a_nro
 }
 int sr_ntt_scale_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, size_t n_limbs, const uint64_t* r, int loc) {
     return scale_impl(ctx, ring, a_inout, n_limbs, r, loc);
+}
+
+/* ---- mailbox: column-sharded commitment over NVLink peer memory -------------------------------------------- */
+static int ensure_counters(sr_ctx* ctx) {
+    if (ctx->commit_counters) return SR_OK;
+    CU(cudaMalloc((void**)&ctx->commit_counters, 2 * sizeof(unsigned)));
+    CU(cudaMemset(ctx->commit_counters, 0, 2 * sizeof(unsigned)));
+    return SR_OK;
+}
+static size_t mailbox_bytes(size_t w, size_t nrows_max, int nranks) {
+    return sr_mailbox::HEADER + (size_t)sr::MAILBOX_DEPTH * nranks * nrows_max * w * 8;
+}
+
+int sr_mailbox_create(sr_ctx* ctx, int ring, size_t nrows_max, int nranks, sr_mailbox** out, unsigned char* handle_out) {
+    if (!ctx || !out) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0 || nrows_max == 0 || nranks < 1 || nranks > sr_mailbox::MAX_RANKS)
+        return fail(ctx, SR_ERR_INVALID, "mailbox: bad ring / nrows_max / nranks");
+    CU(cudaSetDevice(ctx->device));
+    sr_mailbox* mb = new sr_mailbox();
+    mb->ring = ring; mb->nrows_max = nrows_max; mb->nranks = nranks; mb->owner = true;
+    mb->bytes = mailbox_bytes(w, nrows_max, nranks);
+    cudaError_t e = cudaMalloc(&mb->base, mb->bytes);
+    if (e == cudaSuccess) e = cudaMemset(mb->base, 0, mb->bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&mb->sent, 8);
+    if (e == cudaSuccess) e = cudaMemset(mb->sent, 0, 8);
+    if (e == cudaSuccess && handle_out) {
+        cudaIpcMemHandle_t h;
+        e = cudaIpcGetMemHandle(&h, mb->base);
+        if (e == cudaSuccess) memcpy(handle_out, &h, sizeof(h));
+    }
+    if (e != cudaSuccess) {
+        if (mb->base) cudaFree(mb->base);
+        if (mb->sent) cudaFree(mb->sent);
+        delete mb;
+        return cuda_fail(ctx, e, "sr_mailbox_create");
+    }
+    *out = mb;
+    return SR_OK;
+}
+
+int sr_mailbox_open(sr_ctx* ctx, int ring, size_t nrows_max, int nranks, const unsigned char* handle, sr_mailbox** out) {
+    if (!ctx || !out || !handle) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0 || nrows_max == 0 || nranks < 1 || nranks > sr_mailbox::MAX_RANKS)
+        return fail(ctx, SR_ERR_INVALID, "mailbox: bad ring / nrows_max / nranks");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    u64* sent = nullptr;
+    cudaError_t e = cudaMalloc((void**)&sent, 8);
+    if (e == cudaSuccess) e = cudaMemset(sent, 0, 8);
+    if (e != cudaSuccess) {
+        cudaIpcCloseMemHandle(base);
+        if (sent) cudaFree(sent);
+        return cuda_fail(ctx, e, "sr_mailbox_open");
+    }
+    sr_mailbox* mb = new sr_mailbox();
+    mb->sent = sent;
+    mb->ring = ring; mb->nrows_max = nrows_max; mb->nranks = nranks; mb->owner = false;
+    mb->base = base;
+    mb->bytes = mailbox_bytes(w, nrows_max, nranks);
+    *out = mb;
+    return SR_OK;
+}
+
+int sr_mailbox_destroy(sr_ctx* ctx, sr_mailbox* mb) {
+    if (!ctx || !mb) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    if (mb->sent) cudaFree(mb->sent);
+    if (mb->base) {
+        if (mb->owner) CU(cudaFree(mb->base));
+        else CU(cudaIpcCloseMemHandle(mb->base));
+    }
+    delete mb;
+    return SR_OK;
+}
+
+int sr_mailbox_error(sr_ctx* ctx, sr_mailbox* mb, int* timed_out) {
+    if (!ctx || !mb || !timed_out) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(timed_out, mb->err(), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SR_OK;
+}
+
+int sr_commit_send(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v,
+                   size_t v_limbs, sr_mailbox* root_box, int rank, uint64_t epoch) {
+    if (!ctx || !root_box) return SR_ERR_INVALID;
+    if (ring != root_box->ring || nrows == 0 || nrows > root_box->nrows_max || rank < 0 || rank >= root_box->nranks)
+        return fail(ctx, SR_ERR_INVALID, "sr_commit_send: ring / nrows / rank do not fit the mailbox");
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU(cudaSetDevice(ctx->device));
+        int rc = ensure_counters(ctx);
+        if (rc) return rc;
+    }
+    sr::PeerSync ps = {};
+    ps.role = 1;
+    ps.nranks = root_box->nranks;
+    ps.rank = rank;
+    ps.slots = root_box->slots();
+    ps.slot_stride = root_box->nrows_max * elem_limbs(ring);
+    ps.flags = root_box->flags();
+    ps.consumed = root_box->consumed();
+    ps.epoch = epoch;
+    ps.epoch_ctr = root_box->sent;
+    ps.counter = ctx->commit_counters;
+    ps.err = root_box->err();
+    return matvec_impl(ctx, ring, rows, nrows, ncols, v, v_limbs, root_box->slots(), SR_DEVICE, &ps);
+}
+
+int sr_commit_reduce(sr_ctx* ctx, int ring, sr_mailbox* own_box, size_t nrows, uint64_t epoch, uint64_t* out) {
+    if (!ctx || !own_box || !out) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!own_box->owner || ring != own_box->ring || nrows == 0 || nrows > own_box->nrows_max)
+        return fail(ctx, SR_ERR_INVALID, "sr_commit_reduce: needs the mailbox this rank created, matching ring / nrows");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_counters(ctx);
+    if (rc) return rc;
+    sr::PeerSync ps = {};
+    ps.role = 2;
+    ps.nranks = own_box->nranks;
+    ps.slots = own_box->slots();
+    ps.slot_stride = own_box->nrows_max * elem_limbs(ring);
+    ps.flags = own_box->flags();
+    ps.consumed = own_box->consumed();
+    ps.epoch = epoch;
+    ps.epoch_ctr = own_box->consumed();  // device-resident epoch of the root = last epoch summed + 1
+    ps.counter = ctx->commit_counters + 1;
+    ps.err = own_box->err();
+    CU(sr::modsum_launch(ring, own_box->slots(), (size_t)own_box->nranks, own_box->nrows_max, nrows, out, ctx->stream,
+                         &ps));
+    ctx->launches++;
+    return SR_OK;
 }
 
 #define SR_DEFINE_RING(tag, RING)                                                                             \

@@ -519,12 +519,64 @@ matvec_partial_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t 
     }
 }
 
-// out[row] = sum_k parts[k * nrows + row]  (k < nparts).  One warp per (row, slot): the lanes stride over
+// ---- NVLink peer-memory hand-off of the column-sharded commitment -----------------------------------
+// The last kernel of a rank's partial product writes its nrows partial elements STRAIGHT into the root rank's
+// mailbox (peer memory mapped through CUDA IPC; plain stores travel over NVLink), then publishes an epoch flag
+// with release semantics at system scope.  The root's reduction kernel acquires the flags of all ranks and adds the
+// partials mod p.  No NCCL call, no host synchronisation, no extra launch: the exchange is fused into the two
+// kernels that produce and consume the data.  Slots are reused every MAILBOX_DEPTH epochs; a writer first checks
+// the root's `consumed` counter (peer load) so that it never overruns a slot the root has not summed yet.
+SR_D u64 ld_acquire_sys(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SR_D void st_release_sys(u64* p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+SR_D unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;  // a lost peer must not hang the GPU: flag an error
+// spin until *p >= want; false (and *err = 1) on timeout
+SR_D bool spin_until(const u64* p, u64 want, int* err) {
+    if (ld_acquire_sys(p) >= want) return true;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < want) {
+        __nanosleep(200);
+        if (global_ns() - t0 > PEER_TIMEOUT_NS) {
+            atomicExch(err, 1);
+            return false;
+        }
+    }
+    return true;
+}
+// out[row] = sum_k parts[(k * stride_rows + row)]  (k < nparts).  One warp per (row, slot): the lanes stride over
 // the partials, then a shared-memory tree adds the 32 lane sums in a fixed order (deterministic).
+// ps.role 1 (writer): `out` is replaced by this rank's mailbox slot of the epoch; the kernel first makes sure the
+// root has summed the epoch that used the slot before, and publishes the epoch flag once every block has stored.
+// ps.role 2 (root): `parts` is replaced by the epoch's nranks slots; the kernel first acquires all rank flags and
+// publishes `consumed` at the end.
 template <class S>
 __global__ void __launch_bounds__(128)
-sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t nrows, u64* __restrict__ out) {
+sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t stride_rows, size_t nrows,
+                    u64* __restrict__ out, PeerSync ps) {
     __shared__ typename S::Val red[128];
+    u64 epoch = 0;
+    if (ps.role != 0) {  // uniform per launch
+        epoch = ps.epoch ? ps.epoch : *reinterpret_cast<volatile u64*>(ps.epoch_ctr) + 1;
+        const size_t slot0 = (size_t)(epoch % MAILBOX_DEPTH) * ps.nranks;
+        if (ps.role == 1) {
+            out = ps.slots + (slot0 + ps.rank) * ps.slot_stride;
+            if (threadIdx.x == 0 && epoch > (u64)MAILBOX_DEPTH) spin_until(ps.consumed, epoch - MAILBOX_DEPTH, ps.err);
+        } else {
+            parts = ps.slots + slot0 * ps.slot_stride;
+            for (int r = threadIdx.x; r < ps.nranks; r += 128) spin_until(ps.flags + r, epoch, ps.err);  // a lane per rank
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t idx = (size_t)blockIdx.x * 4 + warp;  // (row, slot)
     const bool live = idx < nrows * S::SLOTS;
@@ -532,7 +584,7 @@ sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t nrows, 
     typename S::Val s = S::zero();
     if (live)
         for (size_t k = lane; k < nparts; k += 32)
-            S::acc(s, S::load_cached(parts + (k * nrows + row) * S::ELEM_U64 + slot * S::SLOT_U64));
+            S::acc(s, S::load(parts + (k * stride_rows + row) * S::ELEM_U64 + slot * S::SLOT_U64));
     red[threadIdx.x] = s;
     __syncwarp();
 #pragma unroll
@@ -545,16 +597,42 @@ sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t nrows, 
         __syncwarp();
     }
     if (live && lane == 0) S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, red[threadIdx.x]);
+    if (ps.role != 0) {
+        // every block has read the epoch counter before the last one arrives, so it may be advanced here
+        u64* flag = ps.role == 1 ? ps.flags + ps.rank : ps.consumed;
+        __threadfence_system();  // this thread's stores (possibly to peer memory) before the arrival
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned arrived = atomicAdd(ps.counter, 1u);
+            if (arrived == gridDim.x - 1) {
+                *ps.counter = 0;  // ready for the next launch on this stream
+                if (ps.role == 1) *ps.epoch_ctr = epoch;
+                __threadfence_system();
+                st_release_sys(flag, epoch);
+            }
+        }
+    }
 }
 
 static int mv_grid(int sms) { return sms * 4; }
 
+template <class S>
+static cudaError_t final_sum(const u64* parts, size_t nparts, size_t nrows, u64* out, const PeerSync& ps,
+                             cudaStream_t st) {
+    const size_t n = nrows * S::SLOTS;
+    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(parts, nparts, nrows, nrows, out, ps);
+    return cudaGetLastError();
+}
+
 static cudaError_t gl_matvec_launch(const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v, u64* out,
-                                    void* scratch, cudaStream_t st, int sms, int* launches) {
+                                    void* scratch, cudaStream_t st, int sms, int* launches, const PeerSync& ps) {
     typedef GLSlot S;
     *launches = 0;
     if (nrows == 0) return cudaSuccess;
-    if (ncols == 0) return cudaMemsetAsync(out, 0, nrows * S::ELEM_U64 * 8, st);
+    if (ncols == 0) {  // Sum of nothing = ZERO (a sum over zero partials, so that a mailbox flag is still published)
+        (*launches)++;
+        return final_sum<S>(reinterpret_cast<u64*>(scratch), 0, nrows, out, ps, st);
+    }
     size_t total = ncols * S::SLOTS;
     int grid = mv_grid(sms);  // scratch is sized for mv_grid(sms) partials
     size_t need = (total + GLMV_T - 1) / GLMV_T;
@@ -603,10 +681,8 @@ static cudaError_t gl_matvec_launch(const u64* const* d_rows, size_t nrows, size
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(parts, (size_t)grid, nrows, out);
     (*launches)++;
-    return cudaGetLastError();
+    return final_sum<S>(parts, (size_t)grid, nrows, out, ps, st);
 }
 
 size_t matvec_scratch_bytes(int ring, size_t nrows, int sms) {
@@ -616,10 +692,13 @@ size_t matvec_scratch_bytes(int ring, size_t nrows, int sms) {
 
 template <class S>
 static cudaError_t matvec_launch_t(const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v, u64* out,
-                                   void* scratch, cudaStream_t st, int sms, int* launches) {
+                                   void* scratch, cudaStream_t st, int sms, int* launches, const PeerSync& ps) {
     *launches = 0;
     if (nrows == 0) return cudaSuccess;
-    if (ncols == 0) return cudaMemsetAsync(out, 0, nrows * S::ELEM_U64 * 8, st);  // Sum of nothing = ZERO
+    if (ncols == 0) {  // Sum of nothing = ZERO
+        (*launches)++;
+        return final_sum<S>(reinterpret_cast<u64*>(scratch), 0, nrows, out, ps, st);
+    }
     size_t total = ncols * S::SLOTS;
     int grid = mv_grid(sms);
     size_t need = (total + MV_T - 1) / MV_T;
@@ -632,33 +711,39 @@ static cudaError_t matvec_launch_t(const u64* const* d_rows, size_t nrows, size_
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(parts, (size_t)grid, nrows, out);
     (*launches)++;
-    return cudaGetLastError();
+    return final_sum<S>(parts, (size_t)grid, nrows, out, ps, st);
 }
 
+// ps (optional): `out` is a slot of the root's mailbox; see PeerSync
 cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v, u64* out,
-                          void* scratch, cudaStream_t st, int sms, int* launches) {
+                          void* scratch, cudaStream_t st, int sms, int* launches, const PeerSync* ps) {
+    const PeerSync none = {};
+    const PeerSync& p = ps ? *ps : none;
     switch (ring) {
-    case RING_GL: return gl_matvec_launch(d_rows, nrows, ncols, v, out, scratch, st, sms, launches);
-    case RING_BB: return matvec_launch_t<BBSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches);
-    case RING_SP: return matvec_launch_t<SPSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches);
+    case RING_GL: return gl_matvec_launch(d_rows, nrows, ncols, v, out, scratch, st, sms, launches, p);
+    case RING_BB: return matvec_launch_t<BBSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches, p);
+    case RING_SP: return matvec_launch_t<SPSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches, p);
     }
     return cudaErrorInvalidValue;
 }
 
+// out[i] = sum_r gathered[(r * stride_rows + i)] over nranks partials; ps (optional): the root's mailbox reduction
 template <class S>
-static cudaError_t modsum_t(const u64* g, size_t nranks, size_t nrows, u64* out, cudaStream_t st) {
+static cudaError_t modsum_t(const u64* g, size_t nranks, size_t stride_rows, size_t nrows, u64* out,
+                            const PeerSync& ps, cudaStream_t st) {
     const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(g, nranks, nrows, out);
+    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(g, nranks, stride_rows, nrows, out, ps);
     return cudaGetLastError();
 }
-cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t nrows, u64* out, cudaStream_t st) {
+cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t stride_rows, size_t nrows, u64* out,
+                          cudaStream_t st, const PeerSync* ps) {
+    const PeerSync none = {};
+    const PeerSync& p = ps ? *ps : none;
     switch (ring) {
-    case RING_GL: return modsum_t<GLSlot>(gathered, nranks, nrows, out, st);
-    case RING_BB: return modsum_t<BBSlot>(gathered, nranks, nrows, out, st);
-    case RING_SP: return modsum_t<SPSlot>(gathered, nranks, nrows, out, st);
+    case RING_GL: return modsum_t<GLSlot>(gathered, nranks, stride_rows, nrows, out, p, st);
+    case RING_BB: return modsum_t<BBSlot>(gathered, nranks, stride_rows, nrows, out, p, st);
+    case RING_SP: return modsum_t<SPSlot>(gathered, nranks, stride_rows, nrows, out, p, st);
     }
     return cudaErrorInvalidValue;
 }

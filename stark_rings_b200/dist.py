@@ -5,6 +5,10 @@ computes nrows partial ring elements with sr_matvec_partial, the partials are al
 limbs (an NCCL sum would wrap mod 2^64, not mod p) and rank 0 adds them mod p with sr_modsum_partials.
 The reference has no counterpart (it is single-process); the single-GPU semantics are those of
 Matrix::checked_mul_vec (linear_algebra/src/matrix.rs:168-178).
+
+Two exchange paths: `sharded_commit` (NCCL all-gather of the partials, then sr_modsum_partials on rank 0) and
+`PeerCommit` (the partials are stored straight into the root's HBM over NVLink by the kernel that produces them and
+summed by a kernel that acquires per-rank flags: no collective call on the data path).
 """
 from __future__ import annotations
 
@@ -50,3 +54,97 @@ def sharded_commit(matrix_shard, v_shard, world: int, rank: int, group=None, par
                                          ctypes.c_void_p(out.data_ptr()), L.SR_DEVICE), "sr_modsum_partials")
         return out
     return modsum_fn(gathered, world, nrows)
+
+
+class PeerCommit:
+    """Column-sharded commitment over NVLink peer memory (sr_mailbox_* / sr_commit_* of the C ABI).
+
+    The root rank owns a mailbox in its HBM; every rank maps it through CUDA IPC (the 64-byte handle travels once,
+    at construction, through `exchange`, by default torch.distributed.broadcast_object_list).  Per commitment the last
+    kernel of each rank's partial product stores its nrows partial elements straight into the root's mailbox and
+    publishes an epoch flag; the root's reduction kernel acquires the flags and adds the partials mod p.  No NCCL
+    call and no host synchronisation on the data path.
+
+    `ranks_here` > 1 emulates several ranks inside ONE process on one GPU (tests): the shards are sent one after the
+    other with rank ids 0..ranks_here-1 into the process's own mailbox.
+    """
+
+    def __init__(self, config, nrows_max, world, rank, ctx, root=0, exchange=None, device_epochs=False):
+        """device_epochs: the kernels count the commitments themselves (epoch argument 0), so that every step issues
+        identical launches and can be captured in a CUDA graph."""
+        import ctypes as C
+        from . import _lib as L
+        self.config, self.world, self.rank, self.root, self.ctx = config, world, rank, root, ctx
+        self.nrows_max, self.epoch, self.device_epochs = nrows_max, 0, device_epochs
+        self.box = C.c_void_p()
+        handle = None
+        if rank == root:
+            buf = C.create_string_buffer(L.SR_IPC_HANDLE_BYTES)
+            ctx.check(L.lib.sr_mailbox_create(ctx.h, config.ring_id, nrows_max, world, C.byref(self.box), buf),
+                      "sr_mailbox_create")
+            handle = buf.raw
+        if exchange is None and world > 1:
+            import torch.distributed as dist
+
+            def exchange(h):
+                obj = [h]
+                dist.broadcast_object_list(obj, src=root)
+                return obj[0]
+        if world > 1 and exchange is not None:
+            handle = exchange(handle)
+            if rank != root:
+                ctx.check(L.lib.sr_mailbox_open(ctx.h, config.ring_id, nrows_max, world, handle, C.byref(self.box)),
+                          "sr_mailbox_open")
+
+    def send(self, matrix_shard, v_shard, as_rank=None):
+        """This rank's share of the product, written into the root's mailbox (asynchronous)."""
+        import ctypes as C
+        from . import _lib as L
+        from .rings import _ptr_loc
+        cfg = self.config
+        pv, nv, loc, dev = _ptr_loc(v_shard.data)
+        if loc != L.SR_DEVICE:
+            raise ValueError("PeerCommit works on device-resident shards")
+        ptrs = (C.c_void_p * max(matrix_shard.nrows, 1))()
+        for i, r in enumerate(matrix_shard.vals):
+            ptrs[i] = _ptr_loc(r.data)[0]
+        self.ctx.use_torch_stream()
+        rc = L.lib.sr_commit_send(self.ctx.h, cfg.ring_id, ptrs, matrix_shard.nrows, matrix_shard.ncols, pv, nv,
+                                  self.box, self.rank if as_rank is None else as_rank,
+                                  0 if self.device_epochs else self.epoch)
+        self.ctx.check(rc, "sr_commit_send")
+
+    def reduce(self, nrows, out):
+        """Root only: out <- sum of the partials of the current epoch mod p (asynchronous)."""
+        import ctypes as C
+        from . import _lib as L
+        self.ctx.use_torch_stream()
+        self.ctx.check(L.lib.sr_commit_reduce(self.ctx.h, self.config.ring_id, self.box, nrows,
+                                              0 if self.device_epochs else self.epoch,
+                                              C.c_void_p(out.data_ptr())), "sr_commit_reduce")
+        return out
+
+    def commit(self, matrix_shard, v_shard, out=None):
+        """One commitment: every rank calls it with its column shard; returns the result on the root, None elsewhere."""
+        import torch
+        self.epoch += 1
+        self.send(matrix_shard, v_shard)
+        if self.rank != self.root:
+            return None
+        if out is None:
+            out = torch.empty(matrix_shard.nrows * self.config.limbs, dtype=v_shard.data.dtype,
+                              device=v_shard.data.device)
+        return self.reduce(matrix_shard.nrows, out)
+
+    def timed_out(self) -> bool:
+        import ctypes as C
+        from . import _lib as L
+        flag = C.c_int(0)
+        self.ctx.check(L.lib.sr_mailbox_error(self.ctx.h, self.box, C.byref(flag)), "sr_mailbox_error")
+        return bool(flag.value)
+
+    def close(self):
+        from . import _lib as L
+        if self.box:
+            L.lib.sr_mailbox_destroy(self.ctx.h, self.box)
+            self.box = None
