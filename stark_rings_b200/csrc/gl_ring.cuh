@@ -39,6 +39,9 @@ constexpr int root_exp(int k) {
     return t[k];
 }
 
+#if defined(__CUDACC__)
+static __constant__ u32 c_eps = 0xFFFFFFFFu;  // 2^64 mod p as a constant-bank operand (see plus_eps_if)
+#endif
 #if defined(__CUDA_ARCH__)
 SR_D u64 mk64(u32 lo, u32 hi) { return (u64)lo | ((u64)hi << 32); }
 // x >= p  <=>  hi == 2^32 - 1 and lo != 0, and then x - p = lo - 1: two predicate tests and two predicated
@@ -56,21 +59,39 @@ SR_HD u64 canon(u64 x) { return x >= P ? x - P : x; }
 #endif
 
 #if defined(__CUDA_ARCH__)
+// x + m * (2^32 - 1) for m in {0, 1} when the sum is known not to overflow 64 bits: ONE wide multiply-add on the
+// multiply-add pipe (IMAD.WIDE.U32) instead of a three-instruction carry chain on the ALU pipe, which is the
+// binding unit of every Goldilocks kernel (profiles/r01b_gl_ncu.md)
+// (EPS comes from constant memory: with an immediate, ptxas strength-reduces the product into a four-instruction
+// shift / subtract / carry sequence, which is exactly what this is meant to avoid.)
+SR_D u64 plus_eps_if(u32 lo, u32 hi, u32 m) {
+#if defined(SR_GL_EPS_ON_ALU)
+    // kernels whose binding unit is the multiply-add pipe (the mat-vec family) keep the correction on the ALU pipe
+    u32 r0, r1;
+    asm("sub.cc.u32   %0, %2, %4;\n\t"        // + 2^32 - 1 = - m, + m * 2^32
+        "subc.u32     %1, %3, 0;\n\t"
+        "add.u32      %1, %1, %4;\n\t"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(lo), "r"(hi), "r"(m));
+    return mk64(r0, r1);
+#else
+    u32 r0, r1;  // the lo / hi pair is what ptxas fuses into one IMAD.WIDE.U32 with a 64-bit addend
+    asm("mad.lo.cc.u32   %0, %4, %5, %2;\n\t"
+        "madc.hi.u32     %1, %4, %5, %3;\n\t"
+        : "=&r"(r0), "=r"(r1)
+        : "r"(lo), "r"(hi), "r"(m), "r"(c_eps));
+    return mk64(r0, r1);
+#endif
+}
 // a weak, b canonical -> weak
 SR_D u64 add(u64 a, u64 b) {
-    u32 lo, hi;
-    asm("{\n\t"
-        ".reg .u32 m;\n\t"
-        "add.cc.u32   %0, %2, %4;\n\t"
-        "addc.cc.u32  %1, %3, %5;\n\t"
-        "addc.u32     m, 0, 0;\n\t"          // m = carry (add-flags are never fed to subc)
-        "sub.cc.u32   %0, %0, m;\n\t"        // + EPS = + 2^32 - 1 when the sum wrapped
-        "subc.u32     %1, %1, 0;\n\t"
-        "add.u32      %1, %1, m;\n\t"
-        "}"
-        : "=&r"(lo), "=&r"(hi)
+    u32 lo, hi, m;
+    asm("add.cc.u32   %0, %3, %5;\n\t"
+        "addc.cc.u32  %1, %4, %6;\n\t"
+        "addc.u32     %2, 0, 0;\n\t"          // m = carry (add-flags are never fed to subc)
+        : "=&r"(lo), "=&r"(hi), "=r"(m)
         : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
-    return mk64(lo, hi);
+    return plus_eps_if(lo, hi, m);              // + EPS when the sum wrapped: a + b - 2^64 < p, no second wrap
 }
 SR_D u64 sub(u64 a, u64 b) {
     u32 lo, hi;
@@ -88,19 +109,13 @@ SR_D u64 sub(u64 a, u64 b) {
 }
 // lo + hl * (2^32 - 1) for a 32-bit hl (weak result)
 SR_D u64 add_eps_mul(u64 lo, u32 hl) {
-    u32 r0, r1;
-    asm("{\n\t"
-        ".reg .u32 m;\n\t"
-        "mad.lo.cc.u32   %0, %4, 0xFFFFFFFF, %2;\n\t"
-        "madc.hi.cc.u32  %1, %4, 0xFFFFFFFF, %3;\n\t"
-        "addc.u32        m, 0, 0;\n\t"
-        "sub.cc.u32      %0, %0, m;\n\t"
-        "subc.u32        %1, %1, 0;\n\t"
-        "add.u32         %1, %1, m;\n\t"
-        "}"
-        : "=&r"(r0), "=&r"(r1)
+    u32 r0, r1, m;
+    asm("mad.lo.cc.u32   %0, %5, 0xFFFFFFFF, %3;\n\t"
+        "madc.hi.cc.u32  %1, %5, 0xFFFFFFFF, %4;\n\t"
+        "addc.u32        %2, 0, 0;\n\t"
+        : "=&r"(r0), "=&r"(r1), "=r"(m)
         : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"(hl));
-    return mk64(r0, r1);
+    return plus_eps_if(r0, r1, m);  // the wrapped sum is < hl * EPS <= 2^64 - 2^33 + 1: adding EPS cannot wrap again
 }
 // (hi, lo) = 128-bit value -> weak residue.  2^64 = 2^32 - 1, 2^96 = -1 (mod p).
 SR_D u64 reduce128(u64 lo, u64 hi) {

@@ -11,6 +11,8 @@
 // sum of the multi-GPU commitment (sr_modsum_partials).
 #include <cuda_runtime.h>
 
+#define SR_GL_EPS_ON_ALU  // these kernels are bound by the multiply-add pipe: see gl_ring.cuh plus_eps_if
+
 #include "bb_ring.cuh"
 #include "gl_ring.cuh"
 #include "sp_ring.cuh"

@@ -14,6 +14,8 @@
 // matrices: a handful of entries per row) take the thread-per-(row, slot) kernel; long rows the warp-per-row one.
 #include <cuda_runtime.h>
 
+#define SR_GL_EPS_ON_ALU  // these kernels are bound by the multiply-add pipe: see gl_ring.cuh plus_eps_if
+
 #include "sr_slots.cuh"
 
 namespace sr {
