@@ -93,55 +93,52 @@ SR_HD void row_store(u64* row, const u64 (&c)[D]) {
     for (int i = 0; i < D; i += 2) st2(row + i, c[i], c[i + 1]);
 }
 
-// rowA[6q .. 6q+6) <- x * y modulo X^6 - 2^e_q with x = rowA[6q ..], y = rowB[6q ..]; output CANONICAL.
+// z <- x * y modulo X^6 - 2^E (E a warp-uniform runtime exponent); output CANONICAL.
 // y_1..y_5 are pre-multiplied by rho (five shift-reductions), after which output k is one lazy sum of six products:
 // sum_{i <= k} x_i y_{k-i} + sum_{i > k} x_i (rho y_{k+6-i}).
+SR_HD void sextic_mul(u64 (&z)[6], const u64 (&x)[6], const u64 (&y)[6], int E) {
+    u64 ry[6];
+#pragma unroll
+    for (int i = 1; i < 6; i++) ry[i] = mul_pow2_rt(y[i], E);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+#if defined(__CUDA_ARCH__)
+        Acc d;
+        acc_zero(d);
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc_mad(d, x[i], i <= k ? y[k - i] : ry[k + 6 - i]);
+        z[k] = acc_reduce(d);
+#else
+        u64 acc = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc = add(acc, canon(mul(x[i], i <= k ? y[k - i] : ry[k + 6 - i])));
+        z[k] = canon(acc);
+#endif
+    }
+}
+
+// rowA[6q .. 6q+6) <- rowA[6q ..] * rowB[6q ..] modulo X^6 - 2^e_q for the four quarters
 SR_HD void sextic_products(u64* rowA, const u64* rowB) {
     SR_GL_ROLL
     for (int q = 0; q < 4; q++) {
-        const int E = SR_GL_TAB(sextic_exps)[q];
-        u64 x[6], y[6], ry[6];
+        u64 x[6], y[6], z[6];
 #pragma unroll
         for (int i = 0; i < 6; i += 2) {
             ld2(rowA + 6 * q + i, x[i], x[i + 1]);
             ld2(rowB + 6 * q + i, y[i], y[i + 1]);
         }
-#pragma unroll
-        for (int i = 1; i < 6; i++) ry[i] = mul_pow2_rt(y[i], E);
-        u64 z[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-#if defined(__CUDA_ARCH__)
-            Acc d;
-            acc_zero(d);
-#pragma unroll
-            for (int i = 0; i < 6; i++) acc_mad(d, x[i], i <= k ? y[k - i] : ry[k + 6 - i]);
-            z[k] = acc_reduce(d);
-#else
-            u64 acc = 0;
-#pragma unroll
-            for (int i = 0; i < 6; i++) acc = add(acc, canon(mul(x[i], i <= k ? y[k - i] : ry[k + 6 - i])));
-            z[k] = canon(acc);
-#endif
-        }
+        sextic_mul(z, x, y, SR_GL_TAB(sextic_exps)[q]);
 #pragma unroll
         for (int i = 0; i < 6; i += 2) st2(rowA + 6 * q + i, z[i], z[i + 1]);
     }
 }
 
-// Inverse of crt_stages12 with 2^EXTRA folded into the final scalings, in place on the row.  Input CANONICAL
-// (the sextic products), output canonical.
+// Last inverse stage (ntt.rs:292-318) on the coefficient pairs (i, i + 12), i in [2 t0, 2 t1), two pairs per trip,
+// with 2^EXTRA folded into the scalings; output canonical.
 template <int EXTRA>
-SR_HD void icrt_stages12(u64* row) {
-    {
-        u64 c[D];
-        row_load(c, row);
-        ibfly<0, 6, 22, true>(c);   // ntt.rs:272-290
-        ibfly<12, 6, 14, true>(c);
-        row_store(row, c);
-    }
+SR_HD void final_pairs(u64* row, int t0, int t1) {
     SR_GL_ROLL
-    for (int t = 0; t < 6; t++) {  // ntt.rs:292-318, two coefficient pairs per trip
+    for (int t = t0; t < t1; t++) {
         u64 a[2], b[2], lo[2], hi[2];
         ld2(row + 2 * t, a[0], a[1]);
         ld2(row + 12 + 2 * t, b[0], b[1]);
@@ -156,6 +153,20 @@ SR_HD void icrt_stages12(u64* row) {
         st2(row + 2 * t, lo[0], lo[1]);
         st2(row + 12 + 2 * t, hi[0], hi[1]);
     }
+}
+
+// Inverse of crt_stages12 with 2^EXTRA folded into the final scalings, in place on the row.  Input CANONICAL
+// (the sextic products), output canonical.
+template <int EXTRA>
+SR_HD void icrt_stages12(u64* row) {
+    {
+        u64 c[D];
+        row_load(c, row);
+        ibfly<0, 6, 22, true>(c);   // ntt.rs:272-290
+        ibfly<12, 6, 14, true>(c);
+        row_store(row, c);
+    }
+    final_pairs<EXTRA>(row, 0, 6);
 }
 
 // NTT-form product (ntt_form.rs:159-175 on raw Montgomery limbs) as a real loop, two slots (48 bytes of each row)

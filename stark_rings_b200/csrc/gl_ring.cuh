@@ -186,8 +186,8 @@ SR_HD u64 mulw(u64 x) {  // x * ROOTS_OF_UNITY_24[K]
 }
 
 // (a, b) <- (a + w b, a - w b); a, b weak.  For w = -2^e the two outputs simply swap roles.
-template <int LO, int SPAN, int K>
-SR_HD void bfly(u64 (&c)[D]) {
+template <int LO, int SPAN, int K, int N>
+SR_HD void bfly(u64 (&c)[N]) {
     constexpr int E = root_exp(K);
 #pragma unroll
     for (int i = 0; i < SPAN; i++) {
@@ -198,8 +198,8 @@ SR_HD void bfly(u64 (&c)[D]) {
 }
 // (a, b) <- (a + b, w (a - b)); w = -2^e turns a - b into b - a
 // CANON_IN: the inputs are already canonical (skips two canonicalisations per butterfly)
-template <int LO, int SPAN, int K, bool CANON_IN = false>
-SR_HD void ibfly(u64 (&c)[D]) {
+template <int LO, int SPAN, int K, bool CANON_IN = false, int N = D>
+SR_HD void ibfly(u64 (&c)[N]) {
     constexpr int E = root_exp(K);
 #pragma unroll
     for (int i = 0; i < SPAN; i++) {
