@@ -184,6 +184,17 @@ int sr_matmat(sr_ctx* ctx, int ring, const uint64_t* const* a_rows, size_t a_nro
  * sparse_matrix.rs:298-302) on one row / on the vals array: every NTT-form element of a_inout *= r (one element). */
 int sr_ntt_scale_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, size_t n_limbs, const uint64_t* r, int loc);
 
+/* ---- canonical (de)serialization of batches on the device -------------------------------------
+ * Replaces, for a batch, CanonicalSerialize / CanonicalDeserialize of RqPoly / RqNTT (coeff_form.rs:154-189,
+ * ntt_form.rs:24), i.e. ark-serialize 0.4 on each field element in memory order: the little-endian bytes of the
+ * STANDARD-form integer, ceil(modulus bits / 8) = 8 / 4 / 32 bytes per field element (Goldilocks / BabyBear / Starknet
+ * prime), no length prefix (the u64 prefix of a Vec is the caller's).  sr_deserialize_batch returns SR_ERR_INVALID when
+ * an integer is not below the modulus (SerializationError::InvalidData).  Out of place.  The reference holds no
+ * serialized test vector: the byte format is the restated ark-serialize rule ("parity unpinned"). */
+size_t sr_serialized_bytes(int ring, size_t n_elems);
+int sr_serialize_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint8_t* out_bytes, int loc);
+int sr_deserialize_batch(sr_ctx* ctx, int ring, const uint8_t* in_bytes, size_t n_bytes, uint64_t* out, int loc);
+
 /* ---- per-prime entry points (what each model module binds) --------------------------------- */
 #define SR_DECLARE_RING(tag)                                                                          \
     int sr_##tag##_crt_batch(sr_ctx* ctx, uint64_t* buf, size_t n_limbs, int loc);                   \

@@ -40,6 +40,13 @@ def _bind(path):
     L.sro_matmat.restype = ctypes.c_int
     L.sro_scale.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, u64p]
     L.sro_scale.restype = None
+    u8p = ctypes.POINTER(ctypes.c_uint8)
+    L.sro_fe_bytes.argtypes = [ctypes.c_int]
+    L.sro_fe_bytes.restype = ctypes.c_size_t
+    L.sro_serialize.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, u8p]
+    L.sro_serialize.restype = None
+    L.sro_deserialize.argtypes = [ctypes.c_int, u8p, ctypes.c_size_t, u64p]
+    L.sro_deserialize.restype = ctypes.c_int
     L.sro_crt_stages.argtypes = [ctypes.c_int, u64p]
     L.sro_crt_stages.restype = None
     return L
@@ -141,6 +148,31 @@ def matmat(ring, a_rows, m_rows, L=None):
 def scale(ring, a, r, L=None):
     (L or lib()).sro_scale(RINGS[ring], _p(a), a.size // words(ring), _p(r))
     return a
+
+
+def fe_bytes(ring, L=None):
+    return (L or lib()).sro_fe_bytes(RINGS[ring])
+
+
+def serialize(ring, a, L=None):
+    """n elements (raw limbs) -> uint8 array of their canonical serialization (no length prefix)."""
+    L = L or lib()
+    n = a.size // words(ring)
+    nfe = n * (16 if RINGS[ring] == 2 else words(ring))
+    out = np.zeros(nfe * L.sro_fe_bytes(RINGS[ring]), dtype=np.uint8)
+    L.sro_serialize(RINGS[ring], _p(a), n, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+    return out
+
+
+def deserialize(ring, data, L=None):
+    """uint8 array -> raw limbs; ValueError on an integer >= p (InvalidData)."""
+    L = L or lib()
+    D = 16 if RINGS[ring] == 2 else words(ring)
+    n = data.size // (D * L.sro_fe_bytes(RINGS[ring]))
+    out = np.zeros(n * words(ring), dtype=np.uint64)
+    if L.sro_deserialize(RINGS[ring], data.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), n, _p(out)):
+        raise ValueError("InvalidData")
+    return out
 
 
 def reduce(ring, polys, coeffs_per_poly, L=None):

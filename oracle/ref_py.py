@@ -400,6 +400,29 @@ def scale(M, elems, r):
     return [M.ntt_mul(x, r) for x in elems]
 
 
+def fe_bytes(M):
+    """ark-serialize 0.4 (restated; not vendored in the reference tree): ceil(MODULUS_BIT_SIZE / 8) bytes."""
+    return (M.p.bit_length() + 7) // 8
+
+
+def serialize(M, elems):
+    """CanonicalSerialize of ring elements given as lists of standard-form ints in memory order
+    (coeff_form.rs:154-167 / ntt_form.rs:24): little-endian bytes of each field element, no length prefix."""
+    nb = fe_bytes(M)
+    return b"".join(int(x).to_bytes(nb, "little") for e in elems for x in e)
+
+
+def deserialize(M, data):
+    """CanonicalDeserialize (coeff_form.rs:178-189): ValueError where ark-serialize returns InvalidData."""
+    nb = fe_bytes(M)
+    if len(data) % (nb * M.D):
+        raise ValueError("not a whole number of ring elements")
+    vals = [int.from_bytes(data[i:i + nb], "little") for i in range(0, len(data), nb)]
+    if any(v >= M.p for v in vals):
+        raise ValueError("InvalidData: integer not below the modulus")
+    return [vals[i:i + M.D] for i in range(0, len(vals), M.D)]
+
+
 def to_raw(M, vals):
     """standard-form ints -> flat list of little-endian u64 limbs of x*R mod p (ark-ff MontBackend)."""
     out = []

@@ -489,6 +489,54 @@ void sro_scale(int ring, u64* a, size_t n, const u64* r) {
     for (size_t e = 0; e < n; e++) nttmul1(ring, a + e * w, r);
 }
 
+/* Canonical (de)serialization of n ring elements (coeff_form.rs:154-189, ntt_form.rs:24 through
+ * ark-serialize 0.4, restated: each field element as the little-endian bytes of its standard-form integer, 8 / 4 / 32
+ * bytes for Goldilocks / BabyBear / Starknet prime; no length prefix).  The reference holds no serialized vector:
+ * parity unpinned. */
+size_t sro_fe_bytes(int ring) { return ring == SRO_GL ? 8 : ring == SRO_BB ? 4 : 32; }
+void sro_serialize(int ring, const u64* in, size_t n, unsigned char* out) {
+    pthread_once(&once, init_all);
+    size_t w = sro_elem_words(ring);
+    if (ring == SRO_SP) {
+        fp4 one = {{1, 0, 0, 0}};
+        for (size_t i = 0; i < n * 16; i++) {
+            fp4 r;
+            sp_mul(&r, (const fp4*)in + i, &one); /* x R * 1 / R */
+            memcpy(out + i * 32, r.v, 32);
+        }
+        return;
+    }
+    const f1_ctx* F = ring == SRO_GL ? &GL : &BB;
+    size_t fb = sro_fe_bytes(ring);
+    for (size_t i = 0; i < n * w; i++) {
+        u64 x = f1_mul(F, in[i], 1);
+        memcpy(out + i * fb, &x, fb); /* little-endian host */
+    }
+}
+/* returns 1 (InvalidData) when an integer is not below the modulus */
+int sro_deserialize(int ring, const unsigned char* in, size_t n, u64* out) {
+    pthread_once(&once, init_all);
+    size_t w = sro_elem_words(ring);
+    if (ring == SRO_SP) {
+        for (size_t i = 0; i < n * 16; i++) {
+            fp4 x;
+            memcpy(x.v, in + i * 32, 32);
+            if (fp4_geq(&x, &SP_P)) return 1;
+            sp_mul((fp4*)out + i, &x, &SP_R2);
+        }
+        return 0;
+    }
+    const f1_ctx* F = ring == SRO_GL ? &GL : &BB;
+    size_t fb = sro_fe_bytes(ring);
+    for (size_t i = 0; i < n * w; i++) {
+        u64 x = 0;
+        memcpy(&x, in + i * fb, fb);
+        if (x >= F->p) return 1;
+        out[i] = f1_mul(F, x, F->r2);
+    }
+    return 0;
+}
+
 /* Coefficient-form helpers.  reduce: n polynomials of len field elements (D <= len <= 2D) -> n elements
  * (goldilocks/mod.rs:75-98, babybear/mod.rs:87-110, stark_prime/mod.rs:40-47). */
 void sro_reduce(int ring, const u64* in, size_t n, size_t len, u64* out) {

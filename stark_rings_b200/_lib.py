@@ -69,6 +69,9 @@ _sig("sr_mailbox_destroy", _int, _vp, _vp)
 _sig("sr_mailbox_error", _int, _vp, _vp, ctypes.POINTER(ctypes.c_int))
 _sig("sr_commit_send", _int, _vp, _int, _pp, _sz, _sz, _vp, _sz, _vp, _int, ctypes.c_uint64)
 _sig("sr_commit_reduce", _int, _vp, _int, _vp, _sz, ctypes.c_uint64, _vp)
+_sig("sr_serialized_bytes", _sz, _int, _sz)
+_sig("sr_serialize_batch", _int, _vp, _int, _vp, _sz, _vp, _int)
+_sig("sr_deserialize_batch", _int, _vp, _int, _vp, _sz, _vp, _int)
 SR_IPC_HANDLE_BYTES = 64
 for _tag in ("gl", "bb", "sp"):
     _sig("sr_%s_crt_batch" % _tag, _int, _vp, _vp, _sz, _int)
@@ -85,5 +88,6 @@ EXPORTS = [
     "sr_matvec", "sr_matvec_partial", "sr_modsum_partials", "sr_reduce_batch", "sr_rot_batch",
     "sr_gadget_decompose", "sr_gadget_recompose", "sr_sparse_matvec", "sr_matmat", "sr_ntt_scale_batch",
     "sr_mailbox_create", "sr_mailbox_open", "sr_mailbox_destroy", "sr_mailbox_error", "sr_commit_send", "sr_commit_reduce",
+    "sr_serialized_bytes", "sr_serialize_batch", "sr_deserialize_batch",
 ] + ["sr_%s_%s" % (t, f) for t in ("gl", "bb", "sp")
      for f in ("crt_batch", "icrt_batch", "ntt_mul_batch", "ring_mul_batch", "matvec")]

@@ -35,6 +35,8 @@ cudaError_t sparse_matvec_launch(int ring, const u64* row_ptr, const u64* col_id
 cudaError_t matmat_launch(int ring, const u64* const* a_rows, const u64* const* m_rows, u64* const* out_rows,
                           size_t a_nrows, size_t inner, size_t m_ncols, cudaStream_t st);
 cudaError_t scale_launch(int ring, u64* a, const u64* r, size_t n, cudaStream_t st);
+// canonical (de)serialization (sr_serial.cu): op 0 limbs -> bytes, op 1 bytes -> limbs
+cudaError_t serial_launch(int ring, int op, const void* in, void* out, size_t nfe, int* bad, cudaStream_t st);
 }  // namespace sr
 
 using sr::u64;
@@ -429,6 +431,49 @@ int scale_impl(sr_ctx* ctx, int ring, u64* a, size_t n_limbs, const u64* r, int 
     ctx->launches++;
     CU(cudaMemcpyAsync(a, da, n_limbs * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return SR_OK;
+}
+
+size_t fe_bytes(int ring) { return ring == SR_GOLDILOCKS ? 8 : ring == SR_BABYBEAR ? 4 : ring == SR_STARK ? 32 : 0; }
+
+// op 0: serialize (in = limbs, out = bytes); op 1: deserialize (in = bytes, out = limbs)
+int serial_impl(sr_ctx* ctx, int ring, int op, const void* in, size_t in_len, void* out, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring), fb = fe_bytes(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    const size_t N = (ring == SR_STARK) ? 4 : 1, D = w / N;
+    const size_t per_elem = (op == 0) ? w : D * fb;  // limbs in / bytes in
+    if (in_len % per_elem != 0)
+        return fail(ctx, SR_ERR_BAD_LENGTH, "input length is not a whole number of ring elements");
+    const size_t n = in_len / per_elem, nfe = n * D;
+    if (n == 0) return SR_OK;
+    if (!in || !out || in == out) return fail(ctx, SR_ERR_INVALID, "null or aliased buffer");
+    if (loc != SR_DEVICE && loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
+    const size_t in_bytes = (op == 0) ? in_len * 8 : in_len, out_bytes = (op == 0) ? nfe * fb : n * w * 8;
+    DevTemps tmp;
+    int* dbad = nullptr;
+    const void* kin = in;
+    void* kout = out;
+    if (op == 1) {
+        CU(tmp.alloc((void**)&dbad, sizeof(int)));
+        CU(cudaMemsetAsync(dbad, 0, sizeof(int), st));
+    }
+    if (loc == SR_HOST) {
+        CU(tmp.upload((void**)&kin, in, in_bytes, st));
+        CU(tmp.alloc(&kout, out_bytes));
+    } else if (!aligned16(in) || !aligned16(out)) {
+        return fail(ctx, SR_ERR_INVALID, "device buffers must be 16-byte aligned");
+    }
+    CU(sr::serial_launch(ring, op, kin, kout, nfe, dbad, st));
+    ctx->launches++;
+    if (loc == SR_HOST) CU(cudaMemcpyAsync(out, kout, out_bytes, cudaMemcpyDeviceToHost, st));
+    int bad = 0;
+    if (op == 1) CU(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (op == 1 || loc == SR_HOST) CU(cudaStreamSynchronize(st));
+    if (bad) return fail(ctx, SR_ERR_INVALID, "InvalidData: a serialized integer is not below the modulus");
     return SR_OK;
 }
 
@@ -897,6 +942,17 @@ int sr_commit_reduce(sr_ctx* ctx, int ring, sr_mailbox* own_box, size_t nrows, u
                          &ps));
     ctx->launches++;
     return SR_OK;
+}
+
+size_t sr_serialized_bytes(int ring, size_t n_elems) {
+    const size_t w = elem_limbs(ring);
+    return w ? n_elems * (w / (ring == SR_STARK ? 4 : 1)) * fe_bytes(ring) : 0;
+}
+int sr_serialize_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint8_t* out_bytes, int loc) {
+    return serial_impl(ctx, ring, 0, in, n_limbs, out_bytes, loc);
+}
+int sr_deserialize_batch(sr_ctx* ctx, int ring, const uint8_t* in_bytes, size_t n_bytes, uint64_t* out, int loc) {
+    return serial_impl(ctx, ring, 1, in_bytes, n_bytes, out, loc);
 }
 
 #define SR_DEFINE_RING(tag, RING)                                                                             \

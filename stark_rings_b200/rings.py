@@ -282,6 +282,50 @@ class _RqBase:
         if type(other) is not type(self) or other.config is not self.config:
             raise TypeError("operands must be the same ring type")
 
+    # -- CanonicalSerialize / CanonicalDeserialize (coeff_form.rs:154-189, ntt_form.rs:24), batched on the device ------
+    def serialized_size(self) -> int:
+        """serialized_size (coeff_form.rs:165-167) summed over the batch (no Vec length prefix)."""
+        return int(L.lib.sr_serialized_bytes(self.config.ring_id, len(self)))
+
+    def serialize(self):
+        """The batch as ark-serialize bytes: standard-form little-endian integers, 8 / 4 / 32 bytes per field element,
+        elements back to back.  Returns a uint8 array (numpy for host buffers, CUDA tensor for device buffers)."""
+        p, n, loc, dev = _ptr_loc(self.data)
+        nbytes = self.serialized_size()
+        if loc == L.SR_DEVICE:
+            out = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.data.device)[:nbytes]
+            po = ctypes.c_void_p(out.data_ptr())
+        else:
+            out = np.empty(nbytes, dtype=np.uint8)
+            po = ctypes.c_void_p(out.ctypes.data)
+        c = self.config._ctx(dev, self.ctx)
+        c.check(L.lib.sr_serialize_batch(c.h, self.config.ring_id, p, n, po, loc), "sr_serialize_batch")
+        return out
+
+    @classmethod
+    def deserialize(cls, config, data, ctx=None):
+        """Inverse of serialize; raises StarkRingsError where ark-serialize returns SerializationError::InvalidData
+        (an integer not below the modulus) and LengthPanic on a truncated buffer."""
+        if isinstance(data, np.ndarray):
+            if data.dtype != np.uint8 or not data.flags["C_CONTIGUOUS"]:
+                raise TypeError("host bytes must be a contiguous numpy.uint8 array")
+            pi, nb, loc, dev = ctypes.c_void_p(data.ctypes.data), data.size, L.SR_HOST, None
+        else:
+            if data.dtype != torch.uint8 or not data.is_contiguous():
+                raise TypeError("device bytes must be a contiguous torch.uint8 tensor")
+            pi, nb = ctypes.c_void_p(data.data_ptr()), data.numel()
+            loc, dev = (L.SR_DEVICE, data.device.index) if data.is_cuda else (L.SR_HOST, None)
+        per = int(L.lib.sr_serialized_bytes(config.ring_id, 1))
+        n = nb // per
+        if loc == L.SR_DEVICE:
+            out = torch.empty(n * config.limbs, dtype=torch.int64, device=data.device)
+        else:
+            out = np.empty(n * config.limbs, dtype=np.uint64)
+        c = config._ctx(dev, ctx)
+        c.check(L.lib.sr_deserialize_batch(c.h, config.ring_id, pi, nb, _ptr_loc(out)[0] if n else None, loc),
+                "sr_deserialize_batch")
+        return cls(config, out, ctx)
+
 
 class RqPoly(_RqBase):
     """CyclotomicPolyRingGeneral (coeff_form.rs:31-33), batched."""

@@ -147,3 +147,35 @@ def test_matmat_reference_kat_and_scale(S, name):
     rowh = S.Matrix([S.RqNTT(cfg, a.copy())])
     rowh *= S.RqNTT(cfg, r)
     assert np.array_equal(rowh.vals[0].data, want)
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("n", [1, 3, 1000])
+def test_serialize_deserialize(S, name, n):
+    """batch CanonicalSerialize / CanonicalDeserialize on the device against the oracle, round trip,
+    Ring::ONE -> 01 00 00 ..., and InvalidData for an integer that is not below the modulus."""
+    import torch
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    a = rand_raw(name, n, 900 + n)
+    want = C.serialize(name, a)
+    for device in (None, "cuda"):
+        x = S.RqPoly(cfg, dev(a) if device else a.copy())
+        b = x.serialize()
+        assert x.serialized_size() == want.size
+        assert np.array_equal(b.cpu().numpy() if device else b, want)
+        back = S.RqPoly.deserialize(cfg, b)
+        assert np.array_equal(host(back.data) if device else back.data, a)
+        y = S.RqNTT(cfg, dev(a) if device else a.copy()).serialize()   # same bytes: field elements in memory order
+        assert np.array_equal(y.cpu().numpy() if device else y, want)
+    one = np.array(O.to_raw(M, [1] + [0] * (M.D - 1)), dtype=np.uint64)
+    nb = C.fe_bytes(name)
+    assert S.RqPoly(cfg, dev(one)).serialize().cpu().numpy().tobytes() == b"\x01" + b"\x00" * (M.D * nb - 1)
+    bad = want.copy()
+    bad[:nb] = np.frombuffer(M.p.to_bytes(nb, "little"), dtype=np.uint8)
+    with pytest.raises(S.StarkRingsError):
+        S.RqPoly.deserialize(cfg, torch.from_numpy(bad).cuda())
+    with pytest.raises(S.StarkRingsError):
+        S.RqPoly.deserialize(cfg, bad)
+    with pytest.raises(S.LengthPanic):
+        S.RqPoly.deserialize(cfg, want[:-1].copy())
+    assert S.RqPoly.deserialize(cfg, np.empty(0, dtype=np.uint8)).data.size == 0

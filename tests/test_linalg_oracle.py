@@ -128,3 +128,30 @@ def test_c_equals_python_on_random_ring_values(name):
     assert O.matvec(M, want, v4) == O.matvec(M, a, O.matvec(M, m, v4))
     r = rnd()
     assert np.array_equal(C.scale(name, flat(M, a[0]), raw(M, r)), flat(M, O.scale(M, a[0], r)))
+
+
+# ---- canonical serialization (ark-serialize 0.4 restated; the reference holds no serialized vector) ------
+@pytest.mark.parametrize("name", ALL)
+def test_serialization_oracles(name):
+    M = O.MODELS[name]
+    rng = random.Random(41)
+    nb = {"goldilocks": 8, "babybear": 4, "stark_prime": 32}[name]
+    assert O.fe_bytes(M) == nb == C.fe_bytes(name)
+    elems = [[rng.randrange(M.p) for _ in range(M.D)] for _ in range(5)]
+    elems[0] = [0] * M.D
+    elems[1] = [M.p - 1] * M.D
+    elems[2] = [1] + [0] * (M.D - 1)   # Ring::ONE: the byte 01 followed by zeros
+    data = O.serialize(M, elems)
+    assert len(data) == 5 * M.D * nb
+    assert data[2 * M.D * nb: 3 * M.D * nb] == b"\x01" + b"\x00" * (M.D * nb - 1)
+    assert O.deserialize(M, data) == elems
+    got = C.serialize(name, flat(M, elems))
+    assert got.tobytes() == data
+    assert np.array_equal(C.deserialize(name, got), flat(M, elems))
+    # an integer equal to the modulus is InvalidData
+    bad = bytearray(data)
+    bad[:nb] = M.p.to_bytes(nb, "little") if M.p.bit_length() <= 8 * nb else b"\xff" * nb
+    with pytest.raises(ValueError):
+        O.deserialize(M, bytes(bad))
+    with pytest.raises(ValueError):
+        C.deserialize(name, np.frombuffer(bytes(bad), dtype=np.uint8).copy())
