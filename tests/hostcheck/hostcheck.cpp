@@ -8,6 +8,7 @@
 #include "bb_ring.cuh"
 #include "gl_ring.cuh"
 #include "gl_fused6.cuh"
+#include "sp_quad.cuh"
 #include "sp_half.cuh"
 #include "sp_ring.cuh"
 
@@ -96,6 +97,25 @@ void hc_sp_ring_mul(const uint64_t* a, const uint64_t* b, uint64_t* out) {
     sp::icrt(y); memcpy(out, y, 512);
 }
 
+
+// four-threads-per-element formulation (sp_quad.cuh): the four "threads" in turn, stage by stage
+static void sp_quad_fwd(uint32_t* row) {
+    const uint32_t* wtab = &sp::ROOTS_MONT.w[0][0];
+    for (int s = 0; s < 4; s++) for (int t = 0; t < 4; t++) sp::quad_fwd_stage(row, wtab, s, t);
+}
+static void sp_quad_inv(uint32_t* row) {
+    const uint32_t* wtab = &sp::ROOTS_MONT.w[0][0];
+    for (int s = 0; s < 3; s++) for (int t = 0; t < 4; t++) sp::quad_inv_stage(row, wtab, s, t);
+    for (int t = 0; t < 4; t++) sp::quad_inv_last(row, t);
+}
+void hc_sp_crt_quad(uint64_t* e) { sp_quad_fwd((uint32_t*)e); }
+void hc_sp_icrt_quad(uint64_t* e) { sp_quad_inv((uint32_t*)e); }
+void hc_sp_ring_mul_quad(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    uint32_t ra[128], rb[128]; memcpy(ra, a, 512); memcpy(rb, b, 512);
+    sp_quad_fwd(ra); sp_quad_fwd(rb);
+    for (int t = 0; t < 4; t++) sp::quad_slots(ra, rb, t);
+    sp_quad_inv(ra); memcpy(out, ra, 512);
+}
 
 // two-threads-per-element formulation (sp_half.cuh), both halves in sequence
 static void sp_half_crt_host(sp::Fe (&pos)[2][8], const sp::Fe* e) {

@@ -69,6 +69,14 @@ def test_elementwise_against_oracle(hc, name, tag):
             assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt_half", i)
             x = ea.copy(); hc.hc_sp_icrt_half(_p(x))
             assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt_half", i)
+            # four-threads-per-element formulation (sp_quad.cuh)
+            x = ea.copy(); hc.hc_sp_crt_quad(_p(x))
+            assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt_quad", i)
+            x = ea.copy(); hc.hc_sp_icrt_quad(_p(x))
+            assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt_quad", i)
+            out4 = np.zeros(w, dtype=np.uint64)
+            hc.hc_sp_ring_mul_quad(_p(ea), _p(eb), _p(out4))
+            assert np.array_equal(out4, want_rm[i * w:(i + 1) * w]), ("ring_mul_quad", i)
         if tag == "bb":  # two-threads-per-element formulation used by the fused kernel
             out2 = np.zeros(w, dtype=np.uint64)
             hc.hc_bb_ring_mul_half(_p(ea), _p(eb), _p(out2))
