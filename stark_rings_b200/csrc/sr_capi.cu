@@ -63,6 +63,8 @@ struct sr_ctx {
     size_t mv_rows_cap = 0;
     std::vector<const void*> mv_rows_cached;  // host copy of what mv_rows holds (skip re-upload if unchanged)
     unsigned* commit_counters = nullptr;      // [2] block-arrival counters of the mailbox kernels (send, reduce)
+    int* dflag = nullptr;                     // device error flag of the checking kernels (allocated once)
+    int* hflag = nullptr;                     // its pinned host mirror
 };
 
 // Mailbox of the column-sharded commitment: device memory of ONE rank (the root) that every rank maps
@@ -284,6 +286,25 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
     return SR_OK;
 }
 
+// Device error flag shared by the kernels that report a data-dependent failure (decomposition overflow, column
+// index out of range, integer not below the modulus): allocated once per context, so that such calls cost one small
+// async copy and one stream synchronisation instead of a cudaMalloc / cudaFree pair (which synchronises the device).
+int flag_begin(sr_ctx* ctx, cudaStream_t st) {
+    if (!ctx->dflag) {
+        CU(cudaMalloc((void**)&ctx->dflag, sizeof(int)));
+        CU(cudaMallocHost((void**)&ctx->hflag, sizeof(int)));
+    }
+    CU(cudaMemsetAsync(ctx->dflag, 0, sizeof(int), st));
+    return SR_OK;
+}
+// copies the flag back and waits for the stream; *flag receives its value
+int flag_end(sr_ctx* ctx, cudaStream_t st, int* flag) {
+    CU(cudaMemcpyAsync(ctx->hflag, ctx->dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *flag = *ctx->hflag;
+    return SR_OK;
+}
+
 // Temporary device allocations of one call (host-buffer paths of the linear-algebra entry points)
 struct DevTemps {
     std::vector<void*> ptrs;
@@ -332,9 +353,9 @@ int sparse_matvec_impl(sr_ctx* ctx, int ring, size_t nrows, size_t ncols, const 
     const size_t nnz = (size_t)ends[1];
     if (nnz && (!col_idx || !vals || !v)) return fail(ctx, SR_ERR_INVALID, "null buffer");
     DevTemps tmp;
-    int* dbad = nullptr;
-    CU(tmp.alloc((void**)&dbad, sizeof(int)));
-    CU(cudaMemsetAsync(dbad, 0, sizeof(int), st));
+    int rcf = flag_begin(ctx, st);
+    if (rcf) return rcf;
+    int* dbad = ctx->dflag;
     const u64 *k_rp = row_ptr, *k_ci = col_idx, *k_vals = vals, *k_v = v;
     u64* k_out = out;
     if (loc == SR_HOST) {
@@ -352,8 +373,8 @@ int sparse_matvec_impl(sr_ctx* ctx, int ring, size_t nrows, size_t ncols, const 
     ctx->launches++;
     if (loc == SR_HOST) CU(cudaMemcpyAsync(out, k_out, nrows * w * 8, cudaMemcpyDeviceToHost, st));
     int bad = 0;
-    CU(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    rcf = flag_end(ctx, st, &bad);
+    if (rcf) return rcf;
     if (bad) return fail(ctx, SR_ERR_INVALID, "column index out of range (the reference panics on v[i])");
     return SR_OK;
 }
@@ -458,8 +479,9 @@ int serial_impl(sr_ctx* ctx, int ring, int op, const void* in, size_t in_len, vo
     const void* kin = in;
     void* kout = out;
     if (op == 1) {
-        CU(tmp.alloc((void**)&dbad, sizeof(int)));
-        CU(cudaMemsetAsync(dbad, 0, sizeof(int), st));
+        int rcf = flag_begin(ctx, st);
+        if (rcf) return rcf;
+        dbad = ctx->dflag;
     }
     if (loc == SR_HOST) {
         CU(tmp.upload((void**)&kin, in, in_bytes, st));
@@ -471,8 +493,12 @@ int serial_impl(sr_ctx* ctx, int ring, int op, const void* in, size_t in_len, vo
     ctx->launches++;
     if (loc == SR_HOST) CU(cudaMemcpyAsync(out, kout, out_bytes, cudaMemcpyDeviceToHost, st));
     int bad = 0;
-    if (op == 1) CU(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (op == 1 || loc == SR_HOST) CU(cudaStreamSynchronize(st));
+    if (op == 1) {
+        int rcf = flag_end(ctx, st, &bad);
+        if (rcf) return rcf;
+    } else if (loc == SR_HOST) {
+        CU(cudaStreamSynchronize(st));
+    }
     if (bad) return fail(ctx, SR_ERR_INVALID, "InvalidData: a serialized integer is not below the modulus");
     return SR_OK;
 }
@@ -532,6 +558,9 @@ int sr_destroy(sr_ctx* ctx) {
     }
     if (ctx->mv_scratch) cudaFree(ctx->mv_scratch);
     if (ctx->mv_rows) cudaFree(ctx->mv_rows);
+    if (ctx->commit_counters) cudaFree(ctx->commit_counters);
+    if (ctx->dflag) cudaFree(ctx->dflag);
+    if (ctx->hflag) cudaFreeHost(ctx->hflag);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
     if (ctx->t1) cudaEventDestroy(ctx->t1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -749,33 +778,23 @@ static int decomp_impl(sr_ctx* ctx, int ring, int op, const uint64_t* in, size_t
     const uint64_t b_std = b_lo % p;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
-    int* dflag = nullptr;
-    CU(cudaMalloc(&dflag, sizeof(int)));
-    cudaError_t e = cudaMemsetAsync(dflag, 0, sizeof(int), st);
-    void *din = nullptr, *dout = nullptr;
+    if (loc != SR_DEVICE && loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    int rcf = flag_begin(ctx, st);
+    if (rcf) return rcf;
+    DevTemps tmp;
     const size_t ib = in_limbs * 8, ob = (op == 0 ? n * pad : n) * w * 8;
     const u64* kin = in;
     u64* kout = out;
     if (loc == SR_HOST) {
-        if (e == cudaSuccess) e = cudaMalloc(&din, ib);
-        if (e == cudaSuccess) e = cudaMalloc(&dout, ob);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(din, in, ib, cudaMemcpyHostToDevice, st);
-        kin = (const u64*)din;
-        kout = (u64*)dout;
-    } else if (loc != SR_DEVICE) {
-        cudaFree(dflag);
-        return fail(ctx, SR_ERR_INVALID, "unknown loc");
+        CU(tmp.upload((void**)&kin, in, ib, st));
+        CU(tmp.alloc((void**)&kout, ob));
     }
-    if (e == cudaSuccess) e = sr::decomp_launch(ring, op, kin, kout, n, b_lo, b_std, (int)pad, dflag, st);
-    if (e == cudaSuccess && loc == SR_HOST) e = cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, st);
-    int flag = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // the overflow flag makes this call synchronous
-    cudaFree(dflag);
-    if (din) cudaFree(din);
-    if (dout) cudaFree(dout);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "gadget (de/re)composition");
+    CU(sr::decomp_launch(ring, op, kin, kout, n, b_lo, b_std, (int)pad, ctx->dflag, st));
     ctx->launches++;
+    if (loc == SR_HOST) CU(cudaMemcpyAsync(out, kout, ob, cudaMemcpyDeviceToHost, st));
+    int flag = 0;
+    rcf = flag_end(ctx, st, &flag);  // the overflow flag makes this call synchronous
+    if (rcf) return rcf;
     if (flag) return fail(ctx, SR_ERR_BAD_LENGTH, "padding_size too small for the decomposition (the reference panics)");
     return SR_OK;
 }

@@ -38,7 +38,8 @@ struct BBD {
 
 template <class F>
 __global__ void __launch_bounds__(256)
-decompose_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n, long long b, int pad, int* overflow) {
+decompose_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n, long long b, int shift, int pad,
+                 int* overflow) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * F::D) return;
     const size_t j = idx / F::D;
@@ -50,8 +51,16 @@ decompose_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n, lo
     u64* o = out + (j * (size_t)pad) * F::D + i;
     int t = 0;
     for (; t < pad; t++) {
-        long long rem = cur % b;  // truncating, like Rust
-        long long q = cur / b;
+        long long rem, q;  // truncating division, like Rust's i128 `%` and `/`
+        if (shift >= 0) {  // b = 2^shift (the usual gadget bases): shift and mask on the magnitude, sign restored
+            const unsigned long long mag = cur < 0 ? (unsigned long long)(-cur) : (unsigned long long)cur;
+            const long long r = (long long)(mag & (unsigned long long)(b - 1)), qq = (long long)(mag >> shift);
+            rem = cur < 0 ? -r : r;
+            q = cur < 0 ? -qq : qq;
+        } else {
+            rem = cur % b;
+            q = cur / b;
+        }
         long long digit;
         if ((rem < 0 ? -rem : rem) <= bh) {
             digit = rem;
@@ -88,11 +97,14 @@ cudaError_t decomp_launch(int ring, int op, const u64* in, u64* out, size_t n, u
     if (n == 0) return cudaSuccess;
     const size_t D = ring == RING_GL ? 24 : 72;
     const unsigned grid = (unsigned)((n * D + 255) / 256);
+    int shift = -1;  // log2(b) when b is a power of two
+    if ((b & (b - 1)) == 0)
+        for (shift = 0; (1ull << shift) != b; shift++) {}
     if (ring == RING_GL) {
-        if (op == 0) decompose_kernel<GLD><<<grid, 256, 0, st>>>(in, out, n, (long long)b, pad, overflow);
+        if (op == 0) decompose_kernel<GLD><<<grid, 256, 0, st>>>(in, out, n, (long long)b, shift, pad, overflow);
         else recompose_kernel<GLD><<<grid, 256, 0, st>>>(in, out, n, b_std, pad);
     } else if (ring == RING_BB) {
-        if (op == 0) decompose_kernel<BBD><<<grid, 256, 0, st>>>(in, out, n, (long long)b, pad, overflow);
+        if (op == 0) decompose_kernel<BBD><<<grid, 256, 0, st>>>(in, out, n, (long long)b, shift, pad, overflow);
         else recompose_kernel<BBD><<<grid, 256, 0, st>>>(in, out, n, b_std, pad);
     } else {
         return cudaErrorInvalidValue;
