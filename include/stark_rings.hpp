@@ -10,6 +10,9 @@
 //   ntt_form.rs:159-189   Mul / MulUnchecked                       RqNTT::operator*=, mul_unchecked
 //   coeff_form.rs:250-258 Mul (poly_mul + reduce)                  RqPoly::operator*  (fused kernel)
 //   linear_algebra/src/matrix.rs:168-183  checked/try_mul_vec      Matrix<C>::checked_mul_vec / try_mul_vec
+//   linear_algebra/src/matrix.rs:148-166,207-211  mul_mat, *= R      Matrix<C>::checked_mul_mat / try_mul_mat / operator*=
+//   linear_algebra/src/sparse_matrix.rs:17-21,201-217,298-302     SparseMatrix<C> (CSR image of coeffs)
+//   coeff_form.rs:154-189 CanonicalSerialize / Deserialize         RqPoly / RqNTT ::serialize, ::deserialize (batch)
 //   linear_algebra/src/error.rs:3-8       AlgebraError             DifferentLengths
 // Buffers are raw ark-ff limbs (little-endian u64, Montgomery form) in host memory; every call goes
 // to libstarkrings_cuda.so -- there is no CPU implementation behind this header.
@@ -81,6 +84,28 @@ using StarkRingConfig = RingConfig<SR_STARK, 16, 4, 1>;
 
 template <class C> struct RqNTT;
 
+// SerializationError::InvalidData (an integer not below the modulus)
+struct InvalidData : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+template <class C>
+std::vector<uint8_t> serialize_limbs(const std::vector<uint64_t>& limbs) {
+    auto& c = Context::global();
+    std::vector<uint8_t> out(sr_serialized_bytes(C::ring, limbs.size() / C::LIMBS));
+    c.check(sr_serialize_batch(c.get(), C::ring, limbs.data(), limbs.size(), out.data(), SR_HOST), "serialize");
+    return out;
+}
+template <class C>
+std::vector<uint64_t> deserialize_limbs(const std::vector<uint8_t>& bytes) {
+    auto& c = Context::global();
+    const size_t per = sr_serialized_bytes(C::ring, 1);
+    std::vector<uint64_t> out(bytes.size() / per * C::LIMBS);
+    int rc = sr_deserialize_batch(c.get(), C::ring, bytes.data(), bytes.size(), out.data(), SR_HOST);
+    if (rc == SR_ERR_INVALID) throw InvalidData(sr_last_error(c.get()));
+    c.check(rc, "deserialize");
+    return out;
+}
+
 // A batch of coefficient-form elements over one flat limb buffer (len() == 1: a single element).
 template <class C>
 struct RqPoly {
@@ -102,6 +127,9 @@ struct RqPoly {
         return out;
     }
     bool operator==(const RqPoly& o) const { return limbs == o.limbs; }
+    // CanonicalSerialize of the batch (coeff_form.rs:154-167): standard-form little-endian bytes, no length prefix
+    std::vector<uint8_t> serialize() const { return serialize_limbs<C>(limbs); }
+    static RqPoly deserialize(const std::vector<uint8_t>& bytes) { return RqPoly(deserialize_limbs<C>(bytes)); }
 };
 
 template <class C>
@@ -126,6 +154,14 @@ struct RqNTT {
     RqNTT operator*(const RqNTT& rhs) const { RqNTT t(*this); t *= rhs; return t; }
     RqNTT mul_unchecked(const RqNTT& rhs) const { return *this * rhs; }  // ntt_form.rs:177-189
     bool operator==(const RqNTT& o) const { return limbs == o.limbs; }
+    // every element of the batch *= r, r one element (the body of MulAssign<&R> for the matrix types)
+    void scale(const RqNTT& r) {
+        if (r.len() != 1) throw LengthPanic("the scalar must be one ring element");
+        auto& c = Context::global();
+        c.check(sr_ntt_scale_batch(c.get(), C::ring, limbs.data(), limbs.size(), r.limbs.data(), SR_HOST), "scale");
+    }
+    std::vector<uint8_t> serialize() const { return serialize_limbs<C>(limbs); }
+    static RqNTT deserialize(const std::vector<uint8_t>& bytes) { return RqNTT(deserialize_limbs<C>(bytes)); }
 };
 
 template <class C>
@@ -164,6 +200,70 @@ struct Matrix {
         auto r = checked_mul_vec(v);
         if (!r) throw DifferentLengths(ncols, v.len());
         return *r;
+    }
+    // matrix.rs:148-166: out[i][j] = sum_k self[i][k] * m[k][j]; None when self.ncols != m.nrows
+    std::optional<Matrix> checked_mul_mat(const Matrix& m) const {
+        if (ncols != m.nrows) return std::nullopt;
+        std::vector<RqNTT<C>> out(nrows);
+        std::vector<const uint64_t*> pa(nrows), pm(m.nrows);
+        std::vector<uint64_t*> po(nrows);
+        for (size_t i = 0; i < nrows; i++) {
+            out[i].limbs.resize(m.ncols * C::LIMBS);
+            pa[i] = vals[i].limbs.data();
+            po[i] = out[i].limbs.data();
+        }
+        for (size_t k = 0; k < m.nrows; k++) pm[k] = m.vals[k].limbs.data();
+        auto& c = Context::global();
+        c.check(sr_matmat(c.get(), C::ring, pa.data(), nrows, ncols, pm.data(), m.nrows, m.ncols, po.data(), SR_HOST),
+                "matmat");
+        return Matrix(std::move(out));
+    }
+    Matrix try_mul_mat(const Matrix& m) const {  // matrix.rs:185-188
+        auto r = checked_mul_mat(m);
+        if (!r) throw DifferentLengths(ncols, m.nrows);
+        return std::move(*r);
+    }
+    Matrix& operator*=(const RqNTT<C>& r) {  // matrix.rs:207-211
+        for (auto& row : vals) row.scale(r);
+        return *this;
+    }
+};
+
+// SparseMatrix { nrows, ncols, coeffs: Vec<Vec<(R, usize)>> } (sparse_matrix.rs:17-21) held as the CSR image of coeffs
+template <class C>
+struct SparseMatrix {
+    size_t nrows = 0, ncols = 0;
+    std::vector<uint64_t> row_ptr, col_idx;  // row_ptr: nrows + 1 entry offsets
+    RqNTT<C> vals;                           // nnz elements in row order
+    SparseMatrix(size_t nr, size_t nc, const std::vector<std::vector<std::pair<std::vector<uint64_t>, size_t>>>& coeffs)
+        : nrows(nr), ncols(nc), row_ptr(nr + 1, 0) {
+        for (size_t i = 0; i < coeffs.size(); i++) {
+            for (auto& e : coeffs[i]) {
+                vals.limbs.insert(vals.limbs.end(), e.first.begin(), e.first.end());
+                col_idx.push_back(e.second);
+            }
+            row_ptr[i + 1] = col_idx.size();
+        }
+        for (size_t i = coeffs.size(); i < nr; i++) row_ptr[i + 1] = col_idx.size();  // pad_rows
+    }
+    std::optional<RqNTT<C>> checked_mul_vec(const RqNTT<C>& v) const {  // sparse_matrix.rs:201-212
+        RqNTT<C> out;
+        out.limbs.resize(nrows * C::LIMBS);
+        auto& c = Context::global();
+        int rc = sr_sparse_matvec(c.get(), C::ring, nrows, ncols, row_ptr.data(), col_idx.data(), vals.limbs.data(),
+                                  v.limbs.data(), v.limbs.size(), out.limbs.data(), SR_HOST);
+        if (rc == SR_ERR_BAD_LENGTH) return std::nullopt;
+        c.check(rc, "sparse_matvec");
+        return out;
+    }
+    RqNTT<C> try_mul_vec(const RqNTT<C>& v) const {  // sparse_matrix.rs:214-217
+        auto r = checked_mul_vec(v);
+        if (!r) throw DifferentLengths(ncols, v.len());
+        return *r;
+    }
+    SparseMatrix& operator*=(const RqNTT<C>& r) {  // sparse_matrix.rs:298-302
+        if (vals.len()) vals.scale(r);
+        return *this;
     }
 };
 

@@ -14,6 +14,12 @@ void sro_ntt_mul(int ring, uint64_t* a, const uint64_t* b, size_t n, int threads
 void sro_ring_mul(int ring, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, int threads);
 int sro_matvec(int ring, const uint64_t* const* rows, size_t kappa, size_t ncols, const uint64_t* v, size_t vlen,
                uint64_t* out, int threads);
+int sro_sparse_matvec(int ring, size_t nrows, size_t ncols, const uint64_t* row_ptr, const uint64_t* col_idx,
+                      const uint64_t* vals, const uint64_t* v, size_t vlen, uint64_t* out);
+int sro_matmat(int ring, const uint64_t* const* a_rows, size_t a_nrows, size_t a_ncols, const uint64_t* const* m_rows,
+               size_t m_nrows, size_t m_ncols, uint64_t* const* out_rows);
+void sro_scale(int ring, uint64_t* a, size_t n, const uint64_t* r);
+void sro_serialize(int ring, const uint64_t* in, size_t n, unsigned char* out);
 }
 using namespace stark_rings;
 
@@ -80,6 +86,52 @@ static int run(const char* name) {
     bool err = false;
     try { A.try_mul_vec(shortv); } catch (const DifferentLengths& e) { err = (e.lhs == m && e.rhs == m - 1); }
     CHECK(err);
+    // sparse mat-vec (CSR image of coeffs), mat-mat, scaling
+    {
+        const size_t nr = 9, nc = 7;
+        std::vector<std::vector<std::pair<std::vector<uint64_t>, size_t>>> coeffs(nr);
+        for (size_t i = 0; i < nr; i++)
+            for (size_t e = 0; e < i % 4; e++) coeffs[i].push_back({rand_raw<C>(1), (size_t)(next64() % nc)});
+        SparseMatrix<C> S(nr, nc, coeffs);
+        RqNTT<C> x(rand_raw<C>(nc));
+        std::vector<uint64_t> want_s(nr * C::LIMBS);
+        CHECK(sro_sparse_matvec(C::ring, nr, nc, S.row_ptr.data(), S.col_idx.data(), S.vals.limbs.data(), x.limbs.data(),
+                                nc, want_s.data()) == 0);
+        CHECK(S.try_mul_vec(x).limbs == want_s);
+        CHECK(!S.checked_mul_vec(shortv).has_value());
+        RqNTT<C> r(rand_raw<C>(1));
+        auto want_vals = S.vals.limbs;
+        sro_scale(C::ring, want_vals.data(), S.vals.len(), r.limbs.data());
+        S *= r;
+        CHECK(S.vals.limbs == want_vals);
+        // (kappa x m) * (m x 4)
+        std::vector<RqNTT<C>> mrows;
+        std::vector<const uint64_t*> mp;
+        for (size_t k = 0; k < m; k++) mrows.emplace_back(rand_raw<C>(4));
+        for (auto& rr : mrows) mp.push_back(rr.limbs.data());
+        Matrix<C> M(mrows);
+        std::vector<std::vector<uint64_t>> want_p(kappa, std::vector<uint64_t>(4 * C::LIMBS));
+        std::vector<uint64_t*> wp;
+        for (auto& w : want_p) wp.push_back(w.data());
+        CHECK(sro_matmat(C::ring, ptrs.data(), kappa, m, mp.data(), m, 4, wp.data()) == 0);
+        Matrix<C> P = A.try_mul_mat(M);
+        for (size_t i = 0; i < kappa; i++) CHECK(P.vals[i].limbs == want_p[i]);
+        CHECK(!M.checked_mul_mat(M).has_value());
+    }
+    // canonical serialization round trip against the oracle, InvalidData on 0xff.. bytes
+    {
+        RqPoly<C> pa(a);
+        auto bytes = pa.serialize();
+        std::vector<unsigned char> want_b(bytes.size());
+        sro_serialize(C::ring, a.data(), n, want_b.data());
+        CHECK(bytes == want_b);
+        CHECK(RqPoly<C>::deserialize(bytes).limbs == a);
+        auto bad = bytes;
+        for (size_t i = 0; i < 32; i++) bad[i] = 0xff;
+        bool invalid = false;
+        try { RqPoly<C>::deserialize(bad); } catch (const InvalidData&) { invalid = true; }
+        CHECK(invalid);
+    }
     std::printf("ok %s\n", name);
     return 0;
 }
