@@ -327,3 +327,56 @@ def test_decompose_crt_commit_chain_on_device(S, name):
     A = S.Matrix([S.RqNTT(cfg, dev(r)) for r in rows])
     y = A.try_mul_vec(v)
     assert np.array_equal(host(y.data), want)
+
+
+def test_concurrent_host_threads_one_context_each(S):
+    """SURVEY 8b threading row: with `parallel`, rayon workers call the ring operations concurrently
+    (linear_algebra/src/matrix.rs:174).  The library's contract is one context per host thread (plus an internal mutex
+    per context); four threads, each with its own context and stream, must all get the oracle's bits."""
+    import threading
+    import torch
+    name = "goldilocks"
+    cfg = S.CONFIGS[name]
+    results, errors = {}, []
+
+    def worker(k):
+        try:
+            ctx = S.Context(0)
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                for it in range(5):
+                    a, b = rand_raw(name, 3000 + k, 10 * k + it), rand_raw(name, 3000 + k, 10 * k + it + 5)
+                    out = cfg.ring_mul_batch(dev(a), dev(b), ctx=ctx)
+                    y = cfg.crt_batch(dev(a), ctx=ctx)
+                    stream.synchronize()
+                    ok = np.array_equal(host(out), C.ring_mul(name, a, b, threads=1)) and \
+                        np.array_equal(host(y), C.crt(name, a.copy(), threads=1))
+                    results[(k, it)] = ok
+            ctx.close()
+        except Exception as ex:  # pragma: no cover
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(results) == 20 and all(results.values())
+    # and one SHARED context used from several threads: calls are serialised by its mutex, results still exact
+    shared = S.Context(0)
+    res2 = {}
+
+    def worker2(k):
+        a = rand_raw(name, 500, 77 + k)
+        h = a.copy()
+        cfg.crt_batch(h, ctx=shared)  # host-buffer path: synchronous
+        res2[k] = np.array_equal(h, C.crt(name, a.copy(), threads=1))
+
+    threads = [threading.Thread(target=worker2, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    shared.close()
+    assert len(res2) == 4 and all(res2.values())
