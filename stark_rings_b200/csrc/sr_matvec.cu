@@ -479,7 +479,13 @@ static cudaError_t gl_tma3_launch_rb(int grid, const u64* const* d_rows, size_t 
     return cudaGetLastError();
 }
 
-constexpr int MV_T = 256;  // threads per CTA (multiple of every SLOTS)
+#ifndef SR_MV_T
+#define SR_MV_T 256
+#endif
+#ifndef SR_MV_RB
+#define SR_MV_RB 4
+#endif
+constexpr int MV_T = SR_MV_T;  // threads per CTA (multiple of every SLOTS)
 
 // partial[(blockIdx * nrows + row) * ELEM + slot*SLOT_U64 ...] = CTA-local sum for rows [row0, row0+RB)
 template <class S, int RB>
@@ -706,7 +712,7 @@ static cudaError_t matvec_launch_t(const u64* const* d_rows, size_t nrows, size_
     size_t need = (total + MV_T - 1) / MV_T;
     if ((size_t)grid > need) grid = (int)need;
     u64* parts = reinterpret_cast<u64*>(scratch);
-    constexpr int RB = 4;
+    constexpr int RB = SR_MV_RB;
     for (size_t row0 = 0; row0 < nrows; row0 += RB) {
         matvec_partial_kernel<S, RB><<<grid, MV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, parts);
         (*launches)++;
