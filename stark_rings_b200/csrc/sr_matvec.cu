@@ -561,8 +561,9 @@ SR_D bool spin_until(const u64* p, u64 want, int* err) {
     }
     return true;
 }
-// out[row] = sum_k parts[(k * stride_rows + row)]  (k < nparts).  One warp per (row, slot): the lanes stride over
-// the partials, then a shared-memory tree adds the 32 lane sums in a fixed order (deterministic).
+// out[row] = sum_k parts[(k * stride_rows + row)]  (k < nparts).  One CTA per (row, slot), fixed-order tree: deterministic.
+// (A warp per (row, slot) took 10.6 us for the 296 partials of a kappa = 4 commit, a quarter of the per-rank time at
+// 8 GPUs: 32 warps on the whole GPU, each chaining ten dependent loads.)
 // ps.role 1 (writer): `out` is replaced by this rank's mailbox slot of the epoch; the kernel first makes sure the
 // root has summed the epoch that used the slot before, and publishes the epoch flag once every block has stored.
 // ps.role 2 (root): `parts` is replaced by the epoch's nranks slots; the kernel first acquires all rank flags and
@@ -585,26 +586,25 @@ sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t stride_
         }
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t idx = (size_t)blockIdx.x * 4 + warp;  // (row, slot)
-    const bool live = idx < nrows * S::SLOTS;
-    const size_t row = live ? idx / S::SLOTS : 0, slot = live ? idx % S::SLOTS : 0;
+    // one CTA per (row, slot): the 128 threads stride over the partials (independent loads, two or three each for the
+    // 296 partials of a mat-vec), then a shared-memory tree adds the 128 thread sums in a fixed order
+    const size_t idx = blockIdx.x;  // (row, slot)
+    const size_t row = idx / S::SLOTS, slot = idx % S::SLOTS;
     typename S::Val s = S::zero();
-    if (live)
-        for (size_t k = lane; k < nparts; k += 32)
-            S::acc(s, S::load(parts + (k * stride_rows + row) * S::ELEM_U64 + slot * S::SLOT_U64));
+    for (size_t k = threadIdx.x; k < nparts; k += 128)
+        S::acc(s, S::load(parts + (k * stride_rows + row) * S::ELEM_U64 + slot * S::SLOT_U64));
     red[threadIdx.x] = s;
-    __syncwarp();
+    __syncthreads();
 #pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
-        if (lane < w) {
+    for (int w = 64; w >= 1; w >>= 1) {
+        if ((int)threadIdx.x < w) {
             typename S::Val t = red[threadIdx.x];
             S::acc(t, red[threadIdx.x + w]);
             red[threadIdx.x] = t;
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (live && lane == 0) S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, red[threadIdx.x]);
+    if (threadIdx.x == 0) S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, red[0]);
     if (ps.role != 0) {
         // every block has read the epoch counter before the last one arrives, so it may be advanced here
         u64* flag = ps.role == 1 ? ps.flags + ps.rank : ps.consumed;
@@ -628,7 +628,7 @@ template <class S>
 static cudaError_t final_sum(const u64* parts, size_t nparts, size_t nrows, u64* out, const PeerSync& ps,
                              cudaStream_t st) {
     const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(parts, nparts, nrows, nrows, out, ps);
+    sum_partials_kernel<S><<<(unsigned)n, 128, 0, st>>>(parts, nparts, nrows, nrows, out, ps);
     return cudaGetLastError();
 }
 
@@ -741,7 +741,7 @@ template <class S>
 static cudaError_t modsum_t(const u64* g, size_t nranks, size_t stride_rows, size_t nrows, u64* out,
                             const PeerSync& ps, cudaStream_t st) {
     const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)((n + 3) / 4), 128, 0, st>>>(g, nranks, stride_rows, nrows, out, ps);
+    sum_partials_kernel<S><<<(unsigned)n, 128, 0, st>>>(g, nranks, stride_rows, nrows, out, ps);
     return cudaGetLastError();
 }
 cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t stride_rows, size_t nrows, u64* out,
