@@ -322,6 +322,24 @@ SR_D u64 acc_reduce(const Acc& A) {
     r = sub(r, (u64)l4 << 32);
     return canon(r);
 }
+// canonical residue of (accumulated value) * 2^128, i.e. with the Montgomery factor 2^-64 = 2^128 of a product of two
+// raw limbs folded into the reduction.  With T = 2^32: T^2 = T - 1, T^3 = -1, so T^4 .. T^8 = -T, 1 - T, 1, T, T - 1 and
+//   (l0 + l1 T + l2 T^2 + l3 T^3 + l4 T^4) T^4 = (l2 + l3 T) - l1 (T - 1) - l0 T + l4 (T - 1):
+// three modular additions of canonical terms instead of a reduction followed by a shift-reduction and a negation.
+SR_D u64 acc_reduce_m128(const Acc& A) {
+    u64 c = (u64)A.e1 + A.o1;
+    const u32 l0 = A.e0, l1 = (u32)c;
+    c = (c >> 32) + (u64)A.e2 + A.o2;
+    const u32 l2 = (u32)c;
+    c = (c >> 32) + (u64)A.e3 + A.o3;
+    const u32 l3 = (u32)c;
+    const u32 l4 = (u32)(c >> 32) + A.e4;
+    u64 r = mk64(l2, l3);                  // weak
+    r = sub(r, (u64)l1 * EPS);             // (2^32 - 1)^2 < p: canonical
+    r = sub(r, mk64(0u, l0));              // l0 2^32 <= p - 1: canonical
+    r = add(r, (u64)l4 * EPS);
+    return canon(r);
+}
 #endif
 
 // z = x * y in F_p[u]/(u^3 - 2^RHO_EXP), then times 2^POST_EXP.  Weak in, weak out.
@@ -338,6 +356,12 @@ SR_HD void slot_mul(u64* z, const u64* x, const u64* y) {
     acc_mad(d0, x0, y0); acc_mad(d0, x1, r2); acc_mad(d0, x2, r1);
     acc_mad(d1, x0, y1); acc_mad(d1, x1, y0); acc_mad(d1, x2, r2);
     acc_mad(d2, x0, y2); acc_mad(d2, x1, y1); acc_mad(d2, x2, y0);
+    if (POST_EXP == 128) {  // the Montgomery factor of a raw-limb product rides on the reduction
+        z[0] = acc_reduce_m128(d0);
+        z[1] = acc_reduce_m128(d1);
+        z[2] = acc_reduce_m128(d2);
+        return;
+    }
     c0 = acc_reduce(d0);
     c1 = acc_reduce(d1);
     c2 = acc_reduce(d2);
