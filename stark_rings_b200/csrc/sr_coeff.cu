@@ -57,11 +57,16 @@ struct SPF {
     SR_D static V sub(const V& a, const V& b) { V r; sp::sub(r, a, b); return r; }
 };
 
+constexpr int COEFF_PER_THREAD = 4;
+
 // out[e][i] for i < D from in[e][0 .. len), D <= len <= 2D
 template <class F>
 __global__ void __launch_bounds__(256)
 reduce_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n, int len) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // COEFF_PER_THREAD outputs per thread, one block width apart: coalesced, several independent loads in flight
+#pragma unroll
+  for (int rep = 0; rep < COEFF_PER_THREAD; rep++) {
+    const size_t idx = ((size_t)blockIdx.x * COEFF_PER_THREAD + rep) * 256 + threadIdx.x;
     if (idx >= n * F::D) return;
     const size_t e = idx / F::D;
     const int i = (int)(idx - e * F::D);
@@ -80,13 +85,16 @@ reduce_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n, int l
         r = F::sub(r, get(F::D + i));
     }
     F::store(out + idx * F::N, r);
+  }
 }
 
 // out = X * in (mod Phi), per element
 template <class F>
 __global__ void __launch_bounds__(256)
 rot_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int rep = 0; rep < COEFF_PER_THREAD; rep++) {
+    const size_t idx = ((size_t)blockIdx.x * COEFF_PER_THREAD + rep) * 256 + threadIdx.x;
     if (idx >= n * F::D) return;
     const size_t e = idx / F::D;
     const int i = (int)(idx - e * F::D);
@@ -99,13 +107,14 @@ rot_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
         if (F::PHI3 && i == F::D / 2) r = F::add(r, F::load(c + (size_t)(F::D - 1) * F::N));
     }
     F::store(out + idx * F::N, r);
+  }
 }
 
 template <class F>
 static cudaError_t coeff_launch_t(int op, const u64* in, u64* out, size_t n, int len, cudaStream_t st) {
     const size_t total = n * F::D;
     if (total == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((total + 255) / 256);
+    const unsigned grid = (unsigned)((total + 256 * COEFF_PER_THREAD - 1) / (256 * COEFF_PER_THREAD));
     if (op == 0) reduce_kernel<F><<<grid, 256, 0, st>>>(in, out, n, len);
     else rot_kernel<F><<<grid, 256, 0, st>>>(in, out, n);
     return cudaGetLastError();

@@ -89,23 +89,31 @@ struct SPSer {
     }
 };
 
+constexpr int FE_PER_THREAD = 4;
+
 template <class F>
 __global__ void __launch_bounds__(256)
 serialize_kernel(const u64* __restrict__ in, unsigned char* __restrict__ out, size_t nfe) {
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < nfe) F::ser(in + i * F::LIMBS, out + i * F::BYTES);
+#pragma unroll
+    for (int rep = 0; rep < FE_PER_THREAD; rep++) {  // one block width apart: coalesced, independent loads in flight
+        const size_t i = ((size_t)blockIdx.x * FE_PER_THREAD + rep) * 256 + threadIdx.x;
+        if (i < nfe) F::ser(in + i * F::LIMBS, out + i * F::BYTES);
+    }
 }
 template <class F>
 __global__ void __launch_bounds__(256)
 deserialize_kernel(const unsigned char* __restrict__ in, u64* __restrict__ out, size_t nfe, int* __restrict__ bad) {
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < nfe && !F::de(in + i * F::BYTES, out + i * F::LIMBS)) *bad = 1;
+#pragma unroll
+    for (int rep = 0; rep < FE_PER_THREAD; rep++) {
+        const size_t i = ((size_t)blockIdx.x * FE_PER_THREAD + rep) * 256 + threadIdx.x;
+        if (i < nfe && !F::de(in + i * F::BYTES, out + i * F::LIMBS)) *bad = 1;
+    }
 }
 
 template <class F>
 static cudaError_t serial_t(int op, const void* in, void* out, size_t nfe, int* bad, cudaStream_t st) {
     if (nfe == 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((nfe + 255) / 256);
+    const unsigned grid = (unsigned)((nfe + 256 * FE_PER_THREAD - 1) / (256 * FE_PER_THREAD));
     if (op == 0) serialize_kernel<F><<<grid, 256, 0, st>>>((const u64*)in, (unsigned char*)out, nfe);
     else deserialize_kernel<F><<<grid, 256, 0, st>>>((const unsigned char*)in, (u64*)out, nfe, bad);
     return cudaGetLastError();
