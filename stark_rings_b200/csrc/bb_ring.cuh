@@ -199,6 +199,21 @@ SR_HD void slot_mul_ntt(u32* z, const u32* x, const u32* y) {
     for (int j = 0; j < SLOT; j++) z[3 * (j % 3) + j / 3] = red((u64)zp[j]);
 }
 
+// The same product with ONE of the two 2^-32 factors still missing (result = x y 2^-32 in memory order): sums of such
+// products are finished with a single extra reduction per coefficient (the mat-vec family: nine wide multiply-adds
+// less per product).
+SR_HD void slot_mul_ntt_lazy(u32* z, const u32* x, const u32* y) {
+    u32 xp[SLOT], yp[SLOT], zp[SLOT];
+#pragma unroll
+    for (int j = 0; j < SLOT; j++) {
+        xp[j] = x[3 * (j % 3) + j / 3];
+        yp[j] = y[3 * (j % 3) + j / 3];
+    }
+    slot_mul_pow<w_m32(1)>(zp, xp, yp);
+#pragma unroll
+    for (int j = 0; j < SLOT; j++) z[3 * (j % 3) + j / 3] = zp[j];
+}
+
 // ntt_form.rs:159-175 on the memory layout: a <- a * b slot-wise (raw Montgomery-64 words).
 SR_HD void ntt_mul(u32 (&a)[D], const u32 (&b)[D]) {
 #pragma unroll

@@ -510,12 +510,13 @@ matvec_partial_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t 
             if (rp[r]) a[r] = S::load(rp[r] + g * S::SLOT_U64);
 #pragma unroll
         for (int r = 0; r < RB; r++)
-            if (rp[r]) S::acc(acc[r], S::mul(a[r], x));
+            if (rp[r]) S::acc(acc[r], S::mul_lazy(a[r], x));
     }
     // CTA reduction per slot index: thread t holds slot t % SLOTS
 #pragma unroll
     for (int r = 0; r < RB; r++) {
         if (row0 + r >= nrows) break;
+        S::finish(acc[r]);
         red[threadIdx.x] = acc[r];
         __syncthreads();
         if (threadIdx.x < S::SLOTS) {

@@ -27,6 +27,9 @@ struct GLSlot {
 #pragma unroll
         for (int i = 0; i < 3; i++) s.c[i] = gl::canon(gl::add(s.c[i], x.c[i]));
     }
+    // mul_lazy / finish: a product that may leave a linear factor to be applied once to a sum of products
+    SR_D static Val mul_lazy(const Val& a, const Val& b) { return mul(a, b); }
+    SR_D static void finish(Val&) {}
 };
 struct BBSlot {
     static constexpr int SLOTS = 8, SLOT_U64 = 9, ELEM_U64 = 72;
@@ -60,6 +63,12 @@ struct BBSlot {
 #pragma unroll
         for (int i = 0; i < 9; i++) s.c[i] = bb::add(s.c[i], x.c[i]);
     }
+    // the second 2^-32 of the Montgomery-64 product is applied once per accumulated sum (bb_ring.cuh)
+    SR_D static Val mul_lazy(const Val& a, const Val& b) { Val z; bb::slot_mul_ntt_lazy(z.c, a.c, b.c); return z; }
+    SR_D static void finish(Val& s) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) s.c[i] = bb::red((u64)s.c[i]);
+    }
 };
 struct SPSlot {
     static constexpr int SLOTS = 16, SLOT_U64 = 4, ELEM_U64 = 64;
@@ -90,6 +99,8 @@ struct SPSlot {
     }
     SR_D static Val mul(const Val& a, const Val& b) { Val z; sp::mont_mul(z, a, b); return z; }
     SR_D static void acc(Val& s, const Val& x) { Val t; sp::add(t, s, x); s = t; }
+    SR_D static Val mul_lazy(const Val& a, const Val& b) { return mul(a, b); }
+    SR_D static void finish(Val&) {}
 };
 
 }  // namespace sr

@@ -41,8 +41,9 @@ sparse_matvec_kernel(const u64* __restrict__ row_ptr, const u64* __restrict__ co
         }
         const typename S::Val a = S::load(vals + e * S::ELEM_U64 + slot * S::SLOT_U64);
         const typename S::Val x = S::load_cached(v + c * S::ELEM_U64 + slot * S::SLOT_U64);
-        S::acc(acc, S::mul(a, x));
+        S::acc(acc, S::mul_lazy(a, x));
     }
+    S::finish(acc);
     S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, acc);
 }
 
@@ -70,9 +71,10 @@ sparse_matvec_warp_kernel(const u64* __restrict__ row_ptr, const u64* __restrict
             }
             const typename S::Val a = S::load(vals + e * S::ELEM_U64 + slot * S::SLOT_U64);
             const typename S::Val x = S::load_cached(v + c * S::ELEM_U64 + slot * S::SLOT_U64);
-            S::acc(acc, S::mul(a, x));
+            S::acc(acc, S::mul_lazy(a, x));
         }
     }
+    S::finish(acc);
     red[threadIdx.x] = acc;
     __syncwarp();
     if (live && sub == 0) {
@@ -98,8 +100,9 @@ matmat_kernel(const u64* const* __restrict__ a_rows, const u64* const* __restric
     for (size_t k = 0; k < inner; k++) {
         const typename S::Val a = S::load_cached(arow + k * S::ELEM_U64 + slot * S::SLOT_U64);
         const typename S::Val x = S::load_cached(m_rows[k] + j * S::ELEM_U64 + slot * S::SLOT_U64);
-        S::acc(acc, S::mul(a, x));
+        S::acc(acc, S::mul_lazy(a, x));
     }
+    S::finish(acc);
     S::store(out_rows[i] + j * S::ELEM_U64 + slot * S::SLOT_U64, acc);
 }
 
