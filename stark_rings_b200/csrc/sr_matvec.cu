@@ -338,8 +338,113 @@ gl_matvec_ws_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
     }
 }
 
+// The same with the rows split over G consumer groups (as gl_matvec_tma_kernel): no CTA barrier in the column loop.
+template <int RB, int G>
+__global__ void __launch_bounds__(GLTMA_T * G + 32, 2)
+gl_matvec_wsg_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
+                    const u64* __restrict__ v, u64* __restrict__ partial) {
+    typedef GLSlot S;
+    constexpr int CS = GLTMA_T, NS = GLTMA_NS, RBT = RB / G;
+    static_assert(RB % G == 0, "row split");
+    constexpr uint32_t ROWB = CS * 24;
+    extern __shared__ __align__(128) unsigned char smem[];
+    u64* stage = reinterpret_cast<u64*>(smem);   // [NS][RB + 1][CS * 3]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * (RB + 1) * ROWB);
+    uint64_t* empty = full + NS;
+    __shared__ S::Val red[GLTMA_T];
+
+    const bool producer = threadIdx.x >= CS * G;
+    const int slot = threadIdx.x % CS, grp = threadIdx.x / CS;  // consumers only
+    const size_t total = ncols * S::SLOTS;
+    const size_t nchunks = (total + CS - 1) / CS;
+    const size_t my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], G * CS / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    GLAcc acc[RBT][3];
+#pragma unroll
+    for (int r = 0; r < RBT; r++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) gl_acc_zero(acc[r][k]);
+
+    if (producer) {
+        if (threadIdx.x == CS * G) {
+            for (size_t it = 0; it < my_chunks; it++) {
+                const int s = (int)(it % NS);
+                if (it >= (size_t)NS) mbar_wait(&empty[s], (uint32_t)(((it / NS) - 1) & 1));
+                const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
+                const uint32_t bytes = (uint32_t)(((total - slot0 < (size_t)CS) ? (total - slot0) : (size_t)CS) * 24);
+                mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
+                u64* dst = stage + (size_t)s * (RB + 1) * CS * 3;
+                tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
+#pragma unroll
+                for (int r = 0; r < RB; r++) {
+                    const u64* rp = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
+                    tma_load_1d(dst + (size_t)(r + 1) * CS * 3, rp + slot0 * 3, bytes, &full[s]);
+                }
+            }
+        }
+    } else {
+        for (size_t it = 0; it < my_chunks; it++) {
+            const int s = (int)(it % NS);
+            mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
+            const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
+            const bool live = slot0 + slot < total;
+            const u64* base = stage + (size_t)s * (RB + 1) * CS * 3 + slot * 3;
+            u64 x0 = 0, x1 = 0, x2 = 0, a[RBT][3];
+            if (live) { x0 = base[0]; x1 = base[1]; x2 = base[2]; }
+#pragma unroll
+            for (int r = 0; r < RBT; r++) {
+                const u64* q = base + (size_t)(grp * RBT + r + 1) * CS * 3;
+                a[r][0] = live ? q[0] : 0; a[r][1] = live ? q[1] : 0; a[r][2] = live ? q[2] : 0;
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+            const u64 xr1 = gl::mul_pow2<gl::root_exp(1)>(x1), xr2 = gl::mul_pow2<gl::root_exp(1)>(x2);
+#pragma unroll
+            for (int r = 0; r < RBT; r++) {
+                gl_acc_mad(acc[r][0], a[r][0], x0);
+                gl_acc_mad(acc[r][0], a[r][1], xr2);
+                gl_acc_mad(acc[r][0], a[r][2], xr1);
+                gl_acc_mad(acc[r][1], a[r][0], x1);
+                gl_acc_mad(acc[r][1], a[r][1], x0);
+                gl_acc_mad(acc[r][1], a[r][2], xr2);
+                gl_acc_mad(acc[r][2], a[r][0], x2);
+                gl_acc_mad(acc[r][2], a[r][1], x1);
+                gl_acc_mad(acc[r][2], a[r][2], x0);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; r++) {
+        if (row0 + r >= nrows) break;
+        if (!producer && grp == r / RBT) {
+            S::Val mine;
+#pragma unroll
+            for (int k = 0; k < 3; k++) mine.c[k] = gl_acc_reduce<128>(acc[r % RBT][k]);
+            red[slot] = mine;
+        }
+        __syncthreads();
+        if (threadIdx.x < S::SLOTS) {
+            S::Val sacc = red[threadIdx.x];
+            for (int k = threadIdx.x + S::SLOTS; k < GLTMA_T; k += S::SLOTS) S::acc(sacc, red[k]);
+            S::store(partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, sacc);
+        }
+        __syncthreads();
+    }
+}
+
 #ifndef SR_GLMV_G
 #define SR_GLMV_G 2
+#endif
+// 4-row passes: warp-specialised row-split kernel (no CTA barrier in the column loop) unless -DSR_GLMV_CTASYNC:
+// 0.582 vs 0.567 of the HBM roofline at m = 2^20, 0.652 vs 0.628 at 2^22 (kappa = 4)
+#if !defined(SR_GLMV_CTASYNC) && !defined(SR_GLMV_WSG)
+#define SR_GLMV_WSG
 #endif
 template <int RB>
 static cudaError_t gl_tma_launch_rb(int grid, const u64* const* d_rows, size_t nrows, size_t row0, size_t ncols,
@@ -348,10 +453,17 @@ static cudaError_t gl_tma_launch_rb(int grid, const u64* const* d_rows, size_t n
     // RB = 4: the row-split kernel (the 12-accumulator consumer would spill under the 168-register cap).
     constexpr bool WS = (RB < 4);
     constexpr int G = WS ? 1 : SR_GLMV_G;
+#if defined(SR_GLMV_WSG)
+    void (*kern)(const u64* const*, size_t, size_t, size_t, const u64*, u64*) =
+        WS ? (void (*)(const u64* const*, size_t, size_t, size_t, const u64*, u64*))gl_matvec_ws_kernel<(RB < 4 ? RB : 1)>
+           : (void (*)(const u64* const*, size_t, size_t, size_t, const u64*, u64*))gl_matvec_wsg_kernel<RB, (RB >= 4 ? SR_GLMV_G : 1)>;
+    const int threads = WS ? GLTMA_T + 32 : GLTMA_T * G + 32;
+#else
     void (*kern)(const u64* const*, size_t, size_t, size_t, const u64*, u64*) =
         WS ? (void (*)(const u64* const*, size_t, size_t, size_t, const u64*, u64*))gl_matvec_ws_kernel<(RB < 4 ? RB : 1)>
            : (void (*)(const u64* const*, size_t, size_t, size_t, const u64*, u64*))gl_matvec_tma_kernel<RB, (RB >= 4 ? SR_GLMV_G : 1)>;
     const int threads = WS ? GLTMA_T + 32 : GLTMA_T * G;
+#endif
     const size_t smem = (size_t)GLTMA_NS * (RB + 1) * GLTMA_T * 24 + 2 * GLTMA_NS * sizeof(uint64_t);
     static thread_local bool configured = false;
     if (!configured) {
