@@ -168,7 +168,13 @@ cudaError_t bb_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cu
     switch (op) {
     case OP_CRT: return launch_batch_op<BBPolicy, OP_CRT, SR_BB_T, 3>(a, b, out, n, st, sms);
     case OP_ICRT: return launch_batch_op<BBPolicy, OP_ICRT, SR_BB_T, 3>(a, b, out, n, st, sms);
-    case OP_NTT_MUL: return launch_batch_op<BBPolicy, OP_NTT_MUL, 64, 4>(a, b, out, n, st, sms);  // 0.88 vs 0.80 of roofline at T=128
+#ifndef SR_BB_NM_T
+#define SR_BB_NM_T 64
+#endif
+#ifndef SR_BB_NM_MINB
+#define SR_BB_NM_MINB 4
+#endif
+    case OP_NTT_MUL: return launch_batch_op<BBPolicy, OP_NTT_MUL, SR_BB_NM_T, SR_BB_NM_MINB>(a, b, out, n, st, sms);  // 0.88 vs 0.80 of roofline at T=128
 #if defined(SR_BB_HALFW)
     case OP_RING_MUL: return launch_ring_mul_half_warp<SR_BB_HALF_WARPS, SR_BB_HALF_MINB>(a, b, out, n, st, sms);
 #elif defined(SR_BB_HALF)

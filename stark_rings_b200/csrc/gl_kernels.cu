@@ -4,17 +4,21 @@
 
 namespace sr {
 
+// One warp per CTA, 16 CTAs per SM: the load / transform / store phases of sixteen independent tiles overlap, where
+// four 4-warp CTAs left the SM waiting on global loads (ncu: long_scoreboard 27% of the stall samples in ntt_mul).
+// n = 2^22, T = 128 x 4 -> 64 x 8 -> 32 x 16: ring_mul 0.324 -> 0.334 -> 0.340, ntt_mul 0.648 -> 0.692 -> 0.732,
+// crt 0.763 -> 0.805 -> 0.824, icrt 0.512 -> 0.520 -> 0.519 of the HBM roofline.
 #ifndef SR_GL_T
-#define SR_GL_T 128
+#define SR_GL_T 32
 #endif
 #ifndef SR_GL_RM_T   // fused ring mul: threads per CTA / resident CTAs per SM
-#define SR_GL_RM_T 128
+#define SR_GL_RM_T 32
 #endif
 #ifndef SR_GL_RM_MINB
-#define SR_GL_RM_MINB 4
+#define SR_GL_RM_MINB 16
 #endif
 #ifndef SR_GL_MINB
-#define SR_GL_MINB 4
+#define SR_GL_MINB 16
 #endif
 
 cudaError_t gl_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms) {
