@@ -5,7 +5,9 @@
 // thread, need 168 registers and keep 12 warps per SM; `wait` on the carry chains of the wide multiply-adds is the
 // dominant stall, fewer warps are slower (8 warps: -25%), and more warps are impossible both by registers and by
 // shared memory (two 528-byte rows per element at two threads per element = 14 warps).  Here an element belongs to
-// four consecutive lanes; in every stage thread t owns butterflies 2t and 2t + 1, reads its four operands from the
+// four threads of one warp (thread t of the warp's eight elements sits in lanes 8t .. 8t + 7, so that a quarter-warp
+// touches the same coefficient of eight consecutive rows: conflict-free with the padded rows); in every stage thread t
+// owns butterflies 2t and 2t + 1, reads its four operands from the
 // row, writes them back, and a __syncwarp() separates the stages.  A thread never holds more than four values, the
 // stage body exists once (the stage, the operand and the twiddle are runtime values), so the kernel needs about half
 // the registers and a sixth of the code of the two-thread version and 24 warps fit on an SM.
