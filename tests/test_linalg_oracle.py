@@ -155,3 +155,46 @@ def test_serialization_oracles(name):
         O.deserialize(M, bytes(bad))
     with pytest.raises(ValueError):
         C.deserialize(name, np.frombuffer(bytes(bad), dtype=np.uint8).copy())
+
+
+# ---- randomised shapes (hypothesis): C oracle == Python oracle for the SURVEY 8f-3 / 8f-4 rows -----------------------
+try:
+    from hypothesis import given, settings, strategies as st
+    HAVE_HYPOTHESIS = True
+except Exception:  # pragma: no cover
+    HAVE_HYPOTHESIS = False
+
+
+if HAVE_HYPOTHESIS:
+    @settings(max_examples=12, deadline=None)
+    @given(name=st.sampled_from(ALL), nrows=st.integers(1, 6), ncols=st.integers(1, 6), seed=st.integers(0, 2**31 - 1))
+    def test_sparse_matvec_random_shapes(name, nrows, ncols, seed):
+        M = O.MODELS[name]
+        rng = random.Random(seed)
+        rnd = lambda: [rng.randrange(M.p) for _ in range(M.D)]
+        coeffs = [[(rnd(), rng.randrange(ncols)) for _ in range(rng.randrange(0, 4))] for _ in range(nrows)]
+        v = [rnd() for _ in range(ncols)]
+        want = O.sparse_matvec(M, ncols, coeffs, v)
+        rp, ci, vals = csr(M, coeffs)
+        got = C.sparse_matvec(name, nrows, ncols, rp, ci, vals, flat(M, v))
+        assert np.array_equal(got, flat(M, want))
+        # linearity in the vector: A (v + w) == A v + A w
+        w = [rnd() for _ in range(ncols)]
+        vw = [O.ntt_add(M, a, b) for a, b in zip(v, w)]
+        lhs = O.sparse_matvec(M, ncols, coeffs, vw)
+        rhs = [O.ntt_add(M, a, b) for a, b in zip(want, O.sparse_matvec(M, ncols, coeffs, w))]
+        assert lhs == rhs
+
+    @settings(max_examples=12, deadline=None)
+    @given(name=st.sampled_from(ALL), n=st.integers(0, 4), seed=st.integers(0, 2**31 - 1))
+    def test_serialization_round_trip_random(name, n, seed):
+        M = O.MODELS[name]
+        rng = random.Random(seed)
+        elems = [[rng.randrange(M.p) for _ in range(M.D)] for _ in range(n)]
+        data = O.serialize(M, elems)
+        assert len(data) == n * M.D * O.fe_bytes(M)
+        assert O.deserialize(M, data) == elems
+        if n:
+            got = C.serialize(name, flat(M, elems))
+            assert got.tobytes() == data
+            assert np.array_equal(C.deserialize(name, got), flat(M, elems))
