@@ -42,8 +42,8 @@ constexpr int root_exp(int k) {
 #if defined(__CUDACC__)
 static __constant__ u32 c_eps = 0xFFFFFFFFu;  // 2^64 mod p as a constant-bank operand (see plus_eps_if)
 #endif
+SR_HD u64 mk64(u32 lo, u32 hi) { return (u64)lo | ((u64)hi << 32); }
 #if defined(__CUDA_ARCH__)
-SR_D u64 mk64(u32 lo, u32 hi) { return (u64)lo | ((u64)hi << 32); }
 // x >= p  <=>  hi == 2^32 - 1 and lo != 0, and then x - p = lo - 1: two predicate tests and two predicated
 // word updates instead of a 64-bit compare, a 64-bit subtraction and two selects
 SR_D u64 canon(u64 x) {
@@ -281,7 +281,7 @@ SR_HD void icrt(u64 (&c)[D]) {
     for (int i = 0; i < D; i++) c[i] = canon(o[i]);
 }
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)  // (both nvcc passes: the slot traits of sr_slots.cuh name these types in kernel templates)
 // ---- lazy accumulation of 64 x 64 -> 128-bit products -------------------------------------------
 // The sum is kept UNREDUCED in a 160-bit accumulator held as two interleaved carry-save halves
 // (E: limbs 0..4 takes lo*lo and hi*hi, O: limbs 1..3 takes the two cross products), so every partial

@@ -30,6 +30,27 @@ struct GLSlot {
     // mul_lazy / finish: a product that may leave a linear factor to be applied once to a sum of products
     SR_D static Val mul_lazy(const Val& a, const Val& b) { return mul(a, b); }
     SR_D static void finish(Val&) {}
+    // Accum: a running sum of slot products.  Goldilocks keeps the three output coefficients as UNREDUCED 160-bit
+    // carry-save sums (gl::Acc) and reduces once per result (valid for up to 2^30 products per sum).
+    struct Accum { gl::Acc d[3]; };
+    SR_D static void accum_zero(Accum& A) { gl::acc_zero(A.d[0]); gl::acc_zero(A.d[1]); gl::acc_zero(A.d[2]); }
+    SR_D static void accum_mad(Accum& A, const Val& a, const Val& x) {
+        const u64 r1 = gl::mul_pow2<gl::root_exp(1)>(x.c[1]), r2 = gl::mul_pow2<gl::root_exp(1)>(x.c[2]);  // u^3 = r
+        gl::acc_mad(A.d[0], a.c[0], x.c[0]); gl::acc_mad(A.d[0], a.c[1], r2); gl::acc_mad(A.d[0], a.c[2], r1);
+        gl::acc_mad(A.d[1], a.c[0], x.c[1]); gl::acc_mad(A.d[1], a.c[1], x.c[0]); gl::acc_mad(A.d[1], a.c[2], r2);
+        gl::acc_mad(A.d[2], a.c[0], x.c[2]); gl::acc_mad(A.d[2], a.c[1], x.c[1]); gl::acc_mad(A.d[2], a.c[2], x.c[0]);
+    }
+    SR_D static Val accum_result(const Accum& A) {  // Montgomery layout: products of raw limbs carry 2^-64 = 2^128
+        Val z;
+#pragma unroll
+        for (int i = 0; i < 3; i++) z.c[i] = gl::acc_reduce_m128(A.d[i]);
+        return z;
+    }
+};
+// Accum for the rings without a lazy representation: the running sum is a Val (mul_lazy / acc / finish)
+template <class S>
+struct ValAccum {
+    typename S::Val v;
 };
 struct BBSlot {
     static constexpr int SLOTS = 8, SLOT_U64 = 9, ELEM_U64 = 72;
@@ -69,6 +90,10 @@ struct BBSlot {
 #pragma unroll
         for (int i = 0; i < 9; i++) s.c[i] = bb::red((u64)s.c[i]);
     }
+    typedef ValAccum<BBSlot> Accum;
+    SR_D static void accum_zero(Accum& A) { A.v = zero(); }
+    SR_D static void accum_mad(Accum& A, const Val& a, const Val& x) { acc(A.v, mul_lazy(a, x)); }
+    SR_D static Val accum_result(const Accum& A) { Val r = A.v; finish(r); return r; }
 };
 struct SPSlot {
     static constexpr int SLOTS = 16, SLOT_U64 = 4, ELEM_U64 = 64;
@@ -101,6 +126,10 @@ struct SPSlot {
     SR_D static void acc(Val& s, const Val& x) { Val t; sp::add(t, s, x); s = t; }
     SR_D static Val mul_lazy(const Val& a, const Val& b) { return mul(a, b); }
     SR_D static void finish(Val&) {}
+    typedef ValAccum<SPSlot> Accum;
+    SR_D static void accum_zero(Accum& A) { A.v = zero(); }
+    SR_D static void accum_mad(Accum& A, const Val& a, const Val& x) { acc(A.v, mul(a, x)); }
+    SR_D static Val accum_result(const Accum& A) { return A.v; }
 };
 
 }  // namespace sr

@@ -31,7 +31,8 @@ sparse_matvec_kernel(const u64* __restrict__ row_ptr, const u64* __restrict__ co
     if (idx >= nrows * S::SLOTS) return;
     const size_t row = idx / S::SLOTS;
     const int slot = (int)(idx - row * S::SLOTS);
-    typename S::Val acc = S::zero();
+    typename S::Accum acc;
+    S::accum_zero(acc);
     const u64 e0 = row_ptr[row], e1 = row_ptr[row + 1];
     for (u64 e = e0; e < e1; e++) {
         const u64 c = col_idx[e];
@@ -41,10 +42,9 @@ sparse_matvec_kernel(const u64* __restrict__ row_ptr, const u64* __restrict__ co
         }
         const typename S::Val a = S::load(vals + e * S::ELEM_U64 + slot * S::SLOT_U64);
         const typename S::Val x = S::load_cached(v + c * S::ELEM_U64 + slot * S::SLOT_U64);
-        S::acc(acc, S::mul_lazy(a, x));
+        S::accum_mad(acc, a, x);
     }
-    S::finish(acc);
-    S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, acc);
+    S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, S::accum_result(acc));
 }
 
 // warp per row: lane = (sub, slot); the 32 / SLOTS sub-lanes stride over the row's entries, then the sub-sums are
@@ -60,7 +60,8 @@ sparse_matvec_warp_kernel(const u64* __restrict__ row_ptr, const u64* __restrict
     const int slot = lane % S::SLOTS, sub = lane / S::SLOTS;
     const size_t row = (size_t)blockIdx.x * (SPMV_T / 32) + warp;
     const bool live = row < nrows;
-    typename S::Val acc = S::zero();
+    typename S::Accum acc;
+    S::accum_zero(acc);
     if (live) {
         const u64 e0 = row_ptr[row], e1 = row_ptr[row + 1];
         for (u64 e = e0 + sub; e < e1; e += SUBS) {
@@ -71,11 +72,10 @@ sparse_matvec_warp_kernel(const u64* __restrict__ row_ptr, const u64* __restrict
             }
             const typename S::Val a = S::load(vals + e * S::ELEM_U64 + slot * S::SLOT_U64);
             const typename S::Val x = S::load_cached(v + c * S::ELEM_U64 + slot * S::SLOT_U64);
-            S::acc(acc, S::mul_lazy(a, x));
+            S::accum_mad(acc, a, x);
         }
     }
-    S::finish(acc);
-    red[threadIdx.x] = acc;
+    red[threadIdx.x] = S::accum_result(acc);
     __syncwarp();
     if (live && sub == 0) {
         typename S::Val s = red[threadIdx.x];
@@ -96,14 +96,14 @@ matmat_kernel(const u64* const* __restrict__ a_rows, const u64* const* __restric
     const int slot = (int)(idx - j * S::SLOTS);
     const size_t i = blockIdx.y;
     const u64* arow = a_rows[i];
-    typename S::Val acc = S::zero();
+    typename S::Accum acc;
+    S::accum_zero(acc);
     for (size_t k = 0; k < inner; k++) {
         const typename S::Val a = S::load_cached(arow + k * S::ELEM_U64 + slot * S::SLOT_U64);
         const typename S::Val x = S::load_cached(m_rows[k] + j * S::ELEM_U64 + slot * S::SLOT_U64);
-        S::acc(acc, S::mul_lazy(a, x));
+        S::accum_mad(acc, a, x);
     }
-    S::finish(acc);
-    S::store(out_rows[i] + j * S::ELEM_U64 + slot * S::SLOT_U64, acc);
+    S::store(out_rows[i] + j * S::ELEM_U64 + slot * S::SLOT_U64, S::accum_result(acc));
 }
 
 // a[e] <- a[e] * r for every element e of the batch; thread per (e, slot)
