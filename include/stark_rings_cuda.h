@@ -114,18 +114,28 @@ int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t n
  * One process per GPU.  The ROOT rank creates a mailbox (device memory) and exports its CUDA IPC handle
  * (SR_IPC_HANDLE_BYTES bytes), which the caller ships to the other ranks out of band (MPI, torch.distributed
  * all_gather_object, a pipe ...); they map it with sr_mailbox_open.  Per commitment (epoch = 1, 2, 3 ... the same on
- * every rank):
- *   every rank:  sr_commit_send    its share of the columns -> nrows partial elements, written by the LAST KERNEL of
- *                                  the product straight into the root's mailbox over NVLink, followed by a
+ * every rank) every rank launches ONE kernel per four matrix rows and nothing else:
+ *   other ranks: sr_commit_send    its share of the columns -> nrows partial elements, written by the tail of the
+ *                                  product kernel straight into the root's mailbox over NVLink, followed by a
  *                                  release-flag; no NCCL call, no host synchronisation, no extra kernel launch
- *   root only:   sr_commit_reduce  one kernel that acquires the flags of all ranks and adds the partials mod p
- *                                  (an NCCL sum cannot reduce mod p) into `out` (device memory of the root)
+ *   root:        sr_commit_root    the same for the root's own share; the tail of the root's kernel then acquires the
+ *                                  flags of all ranks and adds the partials mod p (an NCCL sum cannot reduce mod p)
+ *                                  into `out` (device memory of the root)
+ * Alternatively the root calls sr_commit_send like everybody else and then sr_commit_reduce, a separate kernel that
+ * does the acquire + modular sum (what a caller uses when the reduction must run on another stream, and what the
+ * single-GPU emulation of several ranks uses, where the root's share cannot wait for shares enqueued after it).
  * epoch = 0 selects device-resident epochs: each rank's kernels count their own commitments, so a step issues
- * identical launches every time and can be captured in a CUDA graph (every rank must then call sr_commit_send
- * exactly once per commitment, the root sr_commit_reduce once).  Do not mix the two modes on one mailbox.
- * Both calls are asynchronous on the context's stream.  A wait that exceeds 4 s (a lost peer) sets an error flag,
- * readable with sr_mailbox_error, instead of hanging the GPU.  The reference has no counterpart (single process);
- * single-GPU semantics are those of Matrix::checked_mul_vec (matrix.rs:168-178). */
+ * identical launches every time and can be captured in a CUDA graph (every rank must then make exactly one
+ * sr_commit_send / sr_commit_root call per commitment).  Do not mix the two modes on one mailbox.
+ * All calls are asynchronous on the context's stream.  A wait that exceeds the mailbox's budget (default 4 s,
+ * sr_mailbox_set_timeout; a lost peer) sets an error flag, readable with sr_mailbox_error, instead of hanging the
+ * GPU: a writer that timed out does not overwrite the slot and does not publish, a root that timed out fills `out`
+ * with all-ones limbs (not a canonical residue) so that the value cannot pass for a commitment.  Start the first
+ * commitment only after every rank has opened the mailbox (a barrier), or raise the budget above the start-up
+ * skew.  The reference has no counterpart (single process); single-GPU semantics are those of
+ * Matrix::checked_mul_vec (matrix.rs:168-178).
+ * CUDA graphs: the kernels read the context's row-pointer table; a context whose calls were captured must keep
+ * serving that matrix (use one context per captured matrix). */
 typedef struct sr_mailbox sr_mailbox;
 #define SR_IPC_HANDLE_BYTES 64
 int sr_mailbox_create(sr_ctx* ctx, int ring, size_t nrows_max, int nranks, sr_mailbox** out,
@@ -134,8 +144,11 @@ int sr_mailbox_open(sr_ctx* ctx, int ring, size_t nrows_max, int nranks, const u
                     sr_mailbox** out);
 int sr_mailbox_destroy(sr_ctx* ctx, sr_mailbox* box);
 int sr_mailbox_error(sr_ctx* ctx, sr_mailbox* box, int* timed_out); /* synchronises the context's stream */
+int sr_mailbox_set_timeout(sr_ctx* ctx, sr_mailbox* box, uint64_t nanoseconds); /* budget of one in-kernel wait */
 int sr_commit_send(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v,
                    size_t v_limbs, sr_mailbox* root_box, int rank, uint64_t epoch);
+int sr_commit_root(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v,
+                   size_t v_limbs, sr_mailbox* own_box, int rank, uint64_t epoch, uint64_t* out);
 int sr_commit_reduce(sr_ctx* ctx, int ring, sr_mailbox* own_box, size_t nrows, uint64_t epoch, uint64_t* out);
 
 /* ---- coefficient-form helpers next to the hot path (out of place, out != in) ----

@@ -69,6 +69,8 @@ _sig("sr_mailbox_destroy", _int, _vp, _vp)
 _sig("sr_mailbox_error", _int, _vp, _vp, ctypes.POINTER(ctypes.c_int))
 _sig("sr_commit_send", _int, _vp, _int, _pp, _sz, _sz, _vp, _sz, _vp, _int, ctypes.c_uint64)
 _sig("sr_commit_reduce", _int, _vp, _int, _vp, _sz, ctypes.c_uint64, _vp)
+_sig("sr_commit_root", _int, _vp, _int, _pp, _sz, _sz, _vp, _sz, _vp, _int, ctypes.c_uint64, _vp)
+_sig("sr_mailbox_set_timeout", _int, _vp, _vp, ctypes.c_uint64)
 _sig("sr_serialized_bytes", _sz, _int, _sz)
 _sig("sr_serialize_batch", _int, _vp, _int, _vp, _sz, _vp, _int)
 _sig("sr_deserialize_batch", _int, _vp, _int, _vp, _sz, _vp, _int)
@@ -87,7 +89,8 @@ EXPORTS = [
     "sr_timer_start", "sr_timer_stop", "sr_crt_batch", "sr_icrt_batch", "sr_ntt_mul_batch", "sr_ring_mul_batch",
     "sr_matvec", "sr_matvec_partial", "sr_modsum_partials", "sr_reduce_batch", "sr_rot_batch",
     "sr_gadget_decompose", "sr_gadget_recompose", "sr_sparse_matvec", "sr_matmat", "sr_ntt_scale_batch",
-    "sr_mailbox_create", "sr_mailbox_open", "sr_mailbox_destroy", "sr_mailbox_error", "sr_commit_send", "sr_commit_reduce",
+    "sr_mailbox_create", "sr_mailbox_open", "sr_mailbox_destroy", "sr_mailbox_error", "sr_mailbox_set_timeout", "sr_commit_send", "sr_commit_root",
+    "sr_commit_reduce",
     "sr_serialized_bytes", "sr_serialize_batch", "sr_deserialize_batch",
 ] + ["sr_%s_%s" % (t, f) for t in ("gl", "bb", "sp")
      for f in ("crt_batch", "icrt_batch", "ntt_mul_batch", "ring_mul_batch", "matvec")]

@@ -101,14 +101,10 @@ template <int WARPS, int MINB>
 static cudaError_t launch_ring_mul_half_warp(const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms) {
     auto kern = bb_ring_mul_half_warp_kernel<WARPS, MINB>;
     const size_t smem = (size_t)2 * WARPS * 16 * BBPolicy::ROW * sizeof(u32);
-    static thread_local int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    static KernelCache cache;  // per instantiation, per device
+    int blocks_per_sm = 0;
+    cudaError_t e = cache.configure(kern, WARPS * 32, smem, &blocks_per_sm);
+    if (e != cudaSuccess) return e;
     const size_t ntiles = (n + 15) / 16;
     if (ntiles == 0) return cudaSuccess;
     size_t grid = (size_t)sms * blocks_per_sm;
@@ -123,14 +119,10 @@ static cudaError_t launch_ring_mul_half(const u64* a, const u64* b, u64* out, si
     auto kern = bb_ring_mul_half_kernel<WARPS, MINB>;
     constexpr int TE = WARPS * 16;
     const size_t smem = (size_t)2 * TE * BBPolicy::ROW * sizeof(u32);
-    static thread_local int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    static KernelCache cache;  // per instantiation, per device
+    int blocks_per_sm = 0;
+    cudaError_t e = cache.configure(kern, WARPS * 32, smem, &blocks_per_sm);
+    if (e != cudaSuccess) return e;
     const size_t ntiles = (n + TE - 1) / TE;
     if (ntiles == 0) return cudaSuccess;
     size_t grid = (size_t)sms * blocks_per_sm;

@@ -123,14 +123,10 @@ static cudaError_t launch_sp_half(const u64* a, const u64* b, u64* out, size_t n
     auto kern = sp_half_kernel<OP, WARPS, MINB>;
     constexpr int TE = WARPS * 16;
     const size_t smem = (size_t)(OP == OP_RING_MUL ? 2 : 1) * TE * SPPolicy::ROW * sizeof(u32);
-    static thread_local int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    static KernelCache cache;  // per instantiation, per device
+    int blocks_per_sm = 0;
+    cudaError_t e = cache.configure(kern, WARPS * 32, smem, &blocks_per_sm);
+    if (e != cudaSuccess) return e;
     const size_t ntiles = (n + TE - 1) / TE;
     if (ntiles == 0) return cudaSuccess;
     size_t grid = (size_t)sms * blocks_per_sm;
@@ -200,14 +196,10 @@ static cudaError_t launch_sp_quad(const u64* a, const u64* b, u64* out, size_t n
     auto kern = sp_quad_kernel<OP, WARPS, MINB>;
     constexpr int TE = WARPS * 8;
     const size_t smem = 1024 + (size_t)(OP == OP_RING_MUL || OP == OP_NTT_MUL ? 2 : 1) * TE * SPPolicy::ROW * sizeof(u32);
-    static thread_local int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    static KernelCache cache;  // per instantiation, per device
+    int blocks_per_sm = 0;
+    cudaError_t e = cache.configure(kern, WARPS * 32, smem, &blocks_per_sm);
+    if (e != cudaSuccess) return e;
     const size_t ntiles = (n + TE - 1) / TE;
     if (ntiles == 0) return cudaSuccess;
     size_t grid = (size_t)sms * blocks_per_sm;

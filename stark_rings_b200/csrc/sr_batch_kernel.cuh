@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "sr_launch.cuh"
 #include "sr_tile.cuh"
 
 namespace sr {
@@ -76,14 +77,10 @@ cudaError_t launch_batch_op_warp(const u64* a, const u64* b, u64* out, size_t n,
     auto kern = batch_kernel_warp<R, OP, WARPS, MINB>;
     const bool two = (OP == OP_NTT_MUL || OP == OP_RING_MUL);
     const size_t smem = (size_t)(two ? 2 : 1) * WARPS * 32 * R::ROW * sizeof(u32);
-    static thread_local int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, WARPS * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    static KernelCache cache;  // per instantiation, per device
+    int blocks_per_sm = 0;
+    cudaError_t e = cache.configure(kern, WARPS * 32, smem, &blocks_per_sm);
+    if (e != cudaSuccess) return e;
     const size_t ntiles = (n + 31) / 32;
     if (ntiles == 0) return cudaSuccess;
     size_t grid = (size_t)sms * blocks_per_sm;
@@ -98,14 +95,10 @@ cudaError_t launch_batch_op(const u64* a, const u64* b, u64* out, size_t n, cuda
     auto kern = batch_kernel<R, OP, T, MINB>;
     const bool two = (OP == OP_NTT_MUL || OP == OP_RING_MUL);
     const size_t smem = (size_t)(two ? 2 : 1) * T * R::ROW * sizeof(u32);
-    static thread_local int blocks_per_sm = 0;  // per instantiation
-    if (blocks_per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, T, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    static KernelCache cache;  // per instantiation, per device
+    int blocks_per_sm = 0;
+    cudaError_t e = cache.configure(kern, T, smem, &blocks_per_sm);
+    if (e != cudaSuccess) return e;
     const size_t ntiles = (n + T - 1) / T;
     if (ntiles == 0) return cudaSuccess;
     size_t grid = (size_t)sms * blocks_per_sm;

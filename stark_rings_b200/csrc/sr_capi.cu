@@ -21,7 +21,8 @@ cudaError_t sp_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cu
 // scratch (>= matvec_scratch_bytes).  Returns the number of kernels launched via *launches.
 size_t matvec_scratch_bytes(int ring, size_t nrows, int sms);
 cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
-                          u64* out, void* scratch, cudaStream_t st, int sms, int* launches, const PeerSync* ps);
+                          u64* out, void* scratch, unsigned* counter, cudaStream_t st, int sms, int* launches,
+                          const PeerSync* ps);
 cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t stride_rows, size_t nrows, u64* out,
                           cudaStream_t st, const PeerSync* ps);
 // coefficient-form helpers (sr_coeff.cu): op 0 = reduce, op 1 = rot
@@ -62,7 +63,9 @@ struct sr_ctx {
     void* mv_rows = nullptr;  // device copy of the row-pointer table
     size_t mv_rows_cap = 0;
     std::vector<const void*> mv_rows_cached;  // host copy of what mv_rows holds (skip re-upload if unchanged)
-    unsigned* commit_counters = nullptr;      // [2] block-arrival counters of the mailbox kernels (send, reduce)
+    unsigned* commit_counters = nullptr;      // [4] block-arrival tickets: [0] mat-vec tail, [1] mailbox reduction
+    cudaEvent_t ev_stream = nullptr;          // orders a newly selected stream after the previous one (sr_set_stream)
+    std::vector<std::pair<void*, size_t>> pool;  // grow-only device scratch of the host-buffer paths (DevTemps)
     int* dflag = nullptr;                     // device error flag of the checking kernels (allocated once)
     int* hflag = nullptr;                     // its pinned host mirror
 };
@@ -80,6 +83,7 @@ struct sr_mailbox {
     void* base = nullptr;
     size_t bytes = 0;
     u64* sent = nullptr;  // device-LOCAL count of the epochs this process has delivered into this mailbox
+    unsigned long long timeout_ns = 4000000000ull;  // budget of one in-kernel wait (sr_mailbox_set_timeout)
     u64* flags() const { return reinterpret_cast<u64*>(base); }
     u64* consumed() const { return reinterpret_cast<u64*>(base) + MAX_RANKS; }
     int* err() const { return reinterpret_cast<int*>(reinterpret_cast<u64*>(base) + MAX_RANKS + 1); }
@@ -192,6 +196,32 @@ int batch(sr_ctx* ctx, int ring, int op, const u64* a, const u64* b, u64* out, s
     return fail(ctx, SR_ERR_INVALID, "unknown loc");
 }
 
+int ensure_counters(sr_ctx* ctx) {
+    if (ctx->commit_counters) return SR_OK;
+    CU(cudaMalloc((void**)&ctx->commit_counters, 4 * sizeof(unsigned)));
+    CU(cudaMemset(ctx->commit_counters, 0, 4 * sizeof(unsigned)));
+    return SR_OK;
+}
+
+// Grow-only device scratch of the host-buffer paths: slot k serves the k-th temporary of a call.  Calls hold the
+// context mutex and synchronise before they return, so the slots are free again at the next call; no cudaMalloc /
+// cudaFree (which synchronise the whole device) in steady state.
+cudaError_t pool_get(sr_ctx* ctx, size_t k, size_t bytes, void** p) {
+    if (ctx->pool.size() <= k) ctx->pool.resize(k + 1, std::make_pair((void*)nullptr, (size_t)0));
+    auto& slot = ctx->pool[k];
+    if (slot.second < bytes || !slot.first) {
+        if (slot.first) cudaFree(slot.first);
+        slot.first = nullptr;
+        slot.second = 0;
+        const size_t want = bytes < 256 ? 256 : bytes;
+        cudaError_t e = cudaMalloc(&slot.first, want);
+        if (e != cudaSuccess) return e;
+        slot.second = want;
+    }
+    *p = slot.first;
+    return cudaSuccess;
+}
+
 int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, size_t ncols, const u64* v,
                 size_t v_limbs, u64* out, int loc, const sr::PeerSync* ps = nullptr) {
     if (!ctx) return SR_ERR_INVALID;
@@ -222,12 +252,15 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
         CU(cudaMalloc(&ctx->mv_rows, nrows * sizeof(void*)));
         ctx->mv_rows_cap = nrows;
     }
+    int rcc = ensure_counters(ctx);
+    if (rcc) return rcc;
     int launches = 0;
     if (loc == SR_DEVICE) {
         for (size_t i = 0; i < nrows; i++)
             if (!rows[i] || !aligned16(rows[i])) return fail(ctx, SR_ERR_INVALID, "row pointer null or misaligned");
         // the row table is uploaded only when it changed, so a repeated commit with the same matrix issues
-        // kernels only (and can be captured in a CUDA graph)
+        // kernels only (and can be captured in a CUDA graph; a context whose calls were captured must keep serving
+        // the same matrix, because the captured kernels read this context's row table)
         bool same = ctx->mv_rows_cached.size() == nrows;
         for (size_t i = 0; same && i < nrows; i++) same = (ctx->mv_rows_cached[i] == (const void*)rows[i]);
         if (!same) {
@@ -236,53 +269,36 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
                                cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));
         }
-        CU(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, v, out, ctx->mv_scratch, st,
-                             ctx->sms, &launches, ps));
+        CU(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, v, out, ctx->mv_scratch,
+                             ctx->commit_counters, st, ctx->sms, &launches, ps));
         ctx->launches += launches;
         return SR_OK;
     }
     if (loc != SR_HOST || ps) return fail(ctx, SR_ERR_INVALID, "unknown loc");
-    // Host path: whole operands are copied to the device (a commitment matrix is normally kept
-    // resident with SR_DEVICE; this path exists for drop-in completeness).
+    // Host path: whole operands are copied to the device (a commitment matrix is normally kept resident with
+    // SR_DEVICE; this path exists for drop-in completeness).  The device copies live in the context's grow-only
+    // pool: no per-call cudaMalloc / cudaFree.
     const size_t row_bytes = ncols * w * 8;
     std::vector<void*> drows(nrows, nullptr);
     void* dv = nullptr;
     void* dout = nullptr;
-    int rc = SR_OK;
-    auto cleanup = [&]() {
-        for (void* p : drows)
-            if (p) cudaFree(p);
-        if (dv) cudaFree(dv);
-        if (dout) cudaFree(dout);
-    };
-#define CUX(call)                                   \
-    do {                                            \
-        cudaError_t e_ = (call);                    \
-        if (e_ != cudaSuccess) {                    \
-            rc = cuda_fail(ctx, e_, #call);         \
-            cleanup();                              \
-            return rc;                              \
-        }                                           \
-    } while (0)
-    CUX(cudaMalloc(&dout, nrows * w * 8));
+    CU(pool_get(ctx, 0, nrows * w * 8, &dout));
     if (ncols) {
-        CUX(cudaMalloc(&dv, row_bytes));
-        CUX(cudaMemcpyAsync(dv, v, row_bytes, cudaMemcpyHostToDevice, st));
+        CU(pool_get(ctx, 1, row_bytes, &dv));
+        CU(cudaMemcpyAsync(dv, v, row_bytes, cudaMemcpyHostToDevice, st));
         for (size_t i = 0; i < nrows; i++) {
-            if (!rows[i]) { cleanup(); return fail(ctx, SR_ERR_INVALID, "null row pointer"); }
-            CUX(cudaMalloc(&drows[i], row_bytes));
-            CUX(cudaMemcpyAsync(drows[i], rows[i], row_bytes, cudaMemcpyHostToDevice, st));
+            if (!rows[i]) return fail(ctx, SR_ERR_INVALID, "null row pointer");
+            CU(pool_get(ctx, 2 + i, row_bytes, &drows[i]));
+            CU(cudaMemcpyAsync(drows[i], rows[i], row_bytes, cudaMemcpyHostToDevice, st));
         }
     }
     ctx->mv_rows_cached.clear();
-    CUX(cudaMemcpyAsync(ctx->mv_rows, drows.data(), nrows * sizeof(void*), cudaMemcpyHostToDevice, st));
-    CUX(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, (const u64*)dv, (u64*)dout,
-                          ctx->mv_scratch, st, ctx->sms, &launches, nullptr));
+    CU(cudaMemcpyAsync(ctx->mv_rows, drows.data(), nrows * sizeof(void*), cudaMemcpyHostToDevice, st));
+    CU(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, (const u64*)dv, (u64*)dout,
+                         ctx->mv_scratch, ctx->commit_counters, st, ctx->sms, &launches, nullptr));
     ctx->launches += launches;
-    CUX(cudaMemcpyAsync(out, dout, nrows * w * 8, cudaMemcpyDeviceToHost, st));
-    CUX(cudaStreamSynchronize(st));
-#undef CUX
-    cleanup();
+    CU(cudaMemcpyAsync(out, dout, nrows * w * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return SR_OK;
 }
 
@@ -305,18 +321,13 @@ int flag_end(sr_ctx* ctx, cudaStream_t st, int* flag) {
     return SR_OK;
 }
 
-// Temporary device allocations of one call (host-buffer paths of the linear-algebra entry points)
+// Temporary device buffers of one call (host-buffer paths of the linear-algebra entry points), drawn from the
+// context's grow-only pool (pool_get): slot k = the k-th temporary of the call.
 struct DevTemps {
-    std::vector<void*> ptrs;
-    ~DevTemps() {
-        for (void* p : ptrs)
-            if (p) cudaFree(p);
-    }
-    cudaError_t alloc(void** p, size_t bytes) {
-        cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
-        if (e == cudaSuccess) ptrs.push_back(*p);
-        return e;
-    }
+    sr_ctx* ctx;
+    size_t next = 0;
+    explicit DevTemps(sr_ctx* c) : ctx(c) {}
+    cudaError_t alloc(void** p, size_t bytes) { return pool_get(ctx, next++, bytes ? bytes : 16, p); }
     // device copy of a host array (async on st)
     cudaError_t upload(void** p, const void* host, size_t bytes, cudaStream_t st) {
         cudaError_t e = alloc(p, bytes);
@@ -352,7 +363,7 @@ int sparse_matvec_impl(sr_ctx* ctx, int ring, size_t nrows, size_t ncols, const 
     if (ends[0] != 0) return fail(ctx, SR_ERR_INVALID, "row_ptr[0] must be 0");
     const size_t nnz = (size_t)ends[1];
     if (nnz && (!col_idx || !vals || !v)) return fail(ctx, SR_ERR_INVALID, "null buffer");
-    DevTemps tmp;
+    DevTemps tmp(ctx);
     int rcf = flag_begin(ctx, st);
     if (rcf) return rcf;
     int* dbad = ctx->dflag;
@@ -397,7 +408,7 @@ int matmat_impl(sr_ctx* ctx, int ring, const u64* const* a_rows, size_t a_nrows,
         if (!m_rows[k]) return fail(ctx, SR_ERR_INVALID, "null row pointer");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
-    DevTemps tmp;
+    DevTemps tmp(ctx);
     std::vector<const u64*> ha(a_rows, a_rows + a_nrows), hm(m_rows, m_rows + m_nrows);
     std::vector<u64*> ho(out_rows, out_rows + a_nrows);
     if (loc == SR_HOST) {
@@ -444,7 +455,7 @@ int scale_impl(sr_ctx* ctx, int ring, u64* a, size_t n_limbs, const u64* r, int 
     }
     if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
     cudaStream_t st = ctx->own_stream;
-    DevTemps tmp;
+    DevTemps tmp(ctx);
     u64 *da = nullptr, *dr = nullptr;
     CU(tmp.upload((void**)&da, a, n_limbs * 8, st));
     CU(tmp.upload((void**)&dr, r, w * 8, st));
@@ -474,7 +485,7 @@ int serial_impl(sr_ctx* ctx, int ring, int op, const void* in, size_t in_len, vo
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
     const size_t in_bytes = (op == 0) ? in_len * 8 : in_len, out_bytes = (op == 0) ? nfe * fb : n * w * 8;
-    DevTemps tmp;
+    DevTemps tmp(ctx);
     int* dbad = nullptr;
     const void* kin = in;
     void* kout = out;
@@ -531,7 +542,8 @@ int sr_init(int device, sr_ctx** out) {
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreate(&ctx->t0) == cudaSuccess && cudaEventCreate(&ctx->t1) == cudaSuccess;
+              cudaEventCreate(&ctx->t0) == cudaSuccess && cudaEventCreate(&ctx->t1) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < sr_ctx::NBUF; i++)
         ok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -559,6 +571,9 @@ int sr_destroy(sr_ctx* ctx) {
     if (ctx->mv_scratch) cudaFree(ctx->mv_scratch);
     if (ctx->mv_rows) cudaFree(ctx->mv_rows);
     if (ctx->commit_counters) cudaFree(ctx->commit_counters);
+    for (auto& slot : ctx->pool)
+        if (slot.first) cudaFree(slot.first);
+    if (ctx->ev_stream) cudaEventDestroy(ctx->ev_stream);
     if (ctx->dflag) cudaFree(ctx->dflag);
     if (ctx->hflag) cudaFreeHost(ctx->hflag);
     if (ctx->t0) cudaEventDestroy(ctx->t0);
@@ -572,18 +587,34 @@ int sr_destroy(sr_ctx* ctx) {
 
 const char* sr_last_error(sr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+// The context owns single scratch buffers (mat-vec partials, row table, tickets): when the stream changes, the new
+// stream is ordered after the work already enqueued on the old one, so that two calls can never overlap on them.
+static int switch_stream(sr_ctx* ctx, cudaStream_t next) {
+    if (next == ctx->stream) return SR_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(next, &cs) != cudaSuccess) cs = cudaStreamCaptureStatusNone;
+    cudaStreamCaptureStatus co = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &co) != cudaSuccess) co = cudaStreamCaptureStatusNone;
+    cudaGetLastError();
+    if (cs == cudaStreamCaptureStatusNone && co == cudaStreamCaptureStatusNone) {  // (never tie a capture to outside work)
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaEventRecord(ctx->ev_stream, ctx->stream));
+        CU(cudaStreamWaitEvent(next, ctx->ev_stream, 0));
+    }
+    ctx->stream = next;
+    return SR_OK;
+}
+
 int sr_set_stream(sr_ctx* ctx, void* cuda_stream) {
     if (!ctx) return SR_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->stream = (cudaStream_t)cuda_stream;  // NULL is CUDA's (legacy) default stream
-    return SR_OK;
+    return switch_stream(ctx, (cudaStream_t)cuda_stream);  // NULL is CUDA's (legacy) default stream
 }
 
 int sr_reset_stream(sr_ctx* ctx) {
     if (!ctx) return SR_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->stream = ctx->own_stream;
-    return SR_OK;
+    return switch_stream(ctx, ctx->own_stream);
 }
 
 int sr_sync(sr_ctx* ctx) {
@@ -699,16 +730,12 @@ int sr_modsum_partials(sr_ctx* ctx, int ring, const uint64_t* gathered, size_t n
     if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
     void *dg = nullptr, *dout = nullptr;
     const size_t gbytes = nranks * nrows * w * 8, obytes = nrows * w * 8;
-    cudaError_t e = cudaMalloc(&dg, gbytes);
-    if (e == cudaSuccess) e = cudaMalloc(&dout, obytes);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dg, gathered, gbytes, cudaMemcpyHostToDevice, ctx->own_stream);
-    if (e == cudaSuccess)
-        e = sr::modsum_launch(ring, (const u64*)dg, nranks, nrows, nrows, (u64*)dout, ctx->own_stream, nullptr);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, ctx->own_stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);
-    if (dg) cudaFree(dg);
-    if (dout) cudaFree(dout);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "sr_modsum_partials");
+    CU(pool_get(ctx, 0, gbytes, &dg));
+    CU(pool_get(ctx, 1, obytes, &dout));
+    CU(cudaMemcpyAsync(dg, gathered, gbytes, cudaMemcpyHostToDevice, ctx->own_stream));
+    CU(sr::modsum_launch(ring, (const u64*)dg, nranks, nrows, nrows, (u64*)dout, ctx->own_stream, nullptr));
+    CU(cudaMemcpyAsync(out, dout, obytes, cudaMemcpyDeviceToHost, ctx->own_stream));
+    CU(cudaStreamSynchronize(ctx->own_stream));
     ctx->launches++;
     return SR_OK;
 }
@@ -737,15 +764,12 @@ static int coeff_impl(sr_ctx* ctx, int ring, int op, const uint64_t* in, size_t 
     if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
     void *din = nullptr, *dout = nullptr;
     const size_t ib = in_limbs * 8, ob = n * w * 8;
-    cudaError_t e = cudaMalloc(&din, ib);
-    if (e == cudaSuccess) e = cudaMalloc(&dout, ob);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(din, in, ib, cudaMemcpyHostToDevice, ctx->own_stream);
-    if (e == cudaSuccess) e = sr::coeff_launch(ring, op, (const u64*)din, (u64*)dout, n, (int)len, ctx->own_stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->own_stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->own_stream);
-    if (din) cudaFree(din);
-    if (dout) cudaFree(dout);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "coefficient-form helper");
+    CU(pool_get(ctx, 0, ib, &din));
+    CU(pool_get(ctx, 1, ob, &dout));
+    CU(cudaMemcpyAsync(din, in, ib, cudaMemcpyHostToDevice, ctx->own_stream));
+    CU(sr::coeff_launch(ring, op, (const u64*)din, (u64*)dout, n, (int)len, ctx->own_stream));
+    CU(cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, ctx->own_stream));
+    CU(cudaStreamSynchronize(ctx->own_stream));
     ctx->launches++;
     return SR_OK;
 }
@@ -781,7 +805,7 @@ static int decomp_impl(sr_ctx* ctx, int ring, int op, const uint64_t* in, size_t
     if (loc != SR_DEVICE && loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
     int rcf = flag_begin(ctx, st);
     if (rcf) return rcf;
-    DevTemps tmp;
+    DevTemps tmp(ctx);
     const size_t ib = in_limbs * 8, ob = (op == 0 ? n * pad : n) * w * 8;
     const u64* kin = in;
     u64* kout = out;
@@ -822,12 +846,6 @@ int sr_ntt_scale_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, size_t n_limbs,
 }
 
 /* ---- mailbox: column-sharded commitment over NVLink peer memory -------------------------------------------- */
-static int ensure_counters(sr_ctx* ctx) {
-    if (ctx->commit_counters) return SR_OK;
-    CU(cudaMalloc((void**)&ctx->commit_counters, 2 * sizeof(unsigned)));
-    CU(cudaMemset(ctx->commit_counters, 0, 2 * sizeof(unsigned)));
-    return SR_OK;
-}
 static size_t mailbox_bytes(size_t w, size_t nrows_max, int nranks) {
     return sr_mailbox::HEADER + (size_t)sr::MAILBOX_DEPTH * nranks * nrows_max * w * 8;
 }
@@ -912,30 +930,48 @@ int sr_mailbox_error(sr_ctx* ctx, sr_mailbox* mb, int* timed_out) {
     return SR_OK;
 }
 
-int sr_commit_send(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v,
-                   size_t v_limbs, sr_mailbox* root_box, int rank, uint64_t epoch) {
-    if (!ctx || !root_box) return SR_ERR_INVALID;
-    if (ring != root_box->ring || nrows == 0 || nrows > root_box->nrows_max || rank < 0 || rank >= root_box->nranks)
-        return fail(ctx, SR_ERR_INVALID, "sr_commit_send: ring / nrows / rank do not fit the mailbox");
+int sr_mailbox_set_timeout(sr_ctx* ctx, sr_mailbox* mb, uint64_t nanoseconds) {
+    if (!ctx || !mb || nanoseconds == 0) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    mb->timeout_ns = nanoseconds;
+    return SR_OK;
+}
+
+// role 1 (writer) or 3 (root, fused): this rank's share of the product, delivered through the mailbox
+static int commit_product(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols,
+                          const uint64_t* v, size_t v_limbs, sr_mailbox* box, int rank, uint64_t epoch, int role,
+                          uint64_t* out) {
+    if (!ctx || !box) return SR_ERR_INVALID;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        CU(cudaSetDevice(ctx->device));
-        int rc = ensure_counters(ctx);
-        if (rc) return rc;
+        if (ring != box->ring || nrows == 0 || nrows > box->nrows_max || rank < 0 || rank >= box->nranks)
+            return fail(ctx, SR_ERR_INVALID, "commit: ring / nrows / rank do not fit the mailbox");
+        if (role == 3 && (!box->owner || !out))
+            return fail(ctx, SR_ERR_INVALID, "sr_commit_root: needs the mailbox this rank created and an output buffer");
     }
     sr::PeerSync ps = {};
-    ps.role = 1;
-    ps.nranks = root_box->nranks;
+    ps.role = role;
+    ps.nranks = box->nranks;
     ps.rank = rank;
-    ps.slots = root_box->slots();
-    ps.slot_stride = root_box->nrows_max * elem_limbs(ring);
-    ps.flags = root_box->flags();
-    ps.consumed = root_box->consumed();
+    ps.slots = box->slots();
+    ps.slot_stride = box->nrows_max * elem_limbs(ring);
+    ps.flags = box->flags();
+    ps.consumed = box->consumed();
     ps.epoch = epoch;
-    ps.epoch_ctr = root_box->sent;
-    ps.counter = ctx->commit_counters;
-    ps.err = root_box->err();
-    return matvec_impl(ctx, ring, rows, nrows, ncols, v, v_limbs, root_box->slots(), SR_DEVICE, &ps);
+    ps.epoch_ctr = box->sent;
+    ps.err = box->err();
+    ps.timeout_ns = box->timeout_ns;
+    return matvec_impl(ctx, ring, rows, nrows, ncols, v, v_limbs, role == 3 ? out : box->slots(), SR_DEVICE, &ps);
+}
+
+int sr_commit_send(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v,
+                   size_t v_limbs, sr_mailbox* root_box, int rank, uint64_t epoch) {
+    return commit_product(ctx, ring, rows, nrows, ncols, v, v_limbs, root_box, rank, epoch, 1, nullptr);
+}
+
+int sr_commit_root(sr_ctx* ctx, int ring, const uint64_t* const* rows, size_t nrows, size_t ncols, const uint64_t* v,
+                   size_t v_limbs, sr_mailbox* own_box, int rank, uint64_t epoch, uint64_t* out) {
+    return commit_product(ctx, ring, rows, nrows, ncols, v, v_limbs, own_box, rank, epoch, 3, out);
 }
 
 int sr_commit_reduce(sr_ctx* ctx, int ring, sr_mailbox* own_box, size_t nrows, uint64_t epoch, uint64_t* out) {
@@ -957,6 +993,7 @@ int sr_commit_reduce(sr_ctx* ctx, int ring, sr_mailbox* own_box, size_t nrows, u
     ps.epoch_ctr = own_box->consumed();  // device-resident epoch of the root = last epoch summed + 1
     ps.counter = ctx->commit_counters + 1;
     ps.err = own_box->err();
+    ps.timeout_ns = own_box->timeout_ns;
     CU(sr::modsum_launch(ring, own_box->slots(), (size_t)own_box->nranks, own_box->nrows_max, nrows, out, ctx->stream,
                          &ps));
     ctx->launches++;

@@ -33,16 +33,18 @@ enum { OP_CRT = 0, OP_ICRT = 1, OP_NTT_MUL = 2, OP_RING_MUL = 3 };
 
 // Hand-off of a partial commitment through a peer-memory mailbox (sr_matvec.cu).  role 0 = plain kernel.
 struct PeerSync {
-    int role;               // 1: writer (a rank's final partial-sum kernel), 2: the root's reduction kernel
+    int role;               // 1: writer (the tail of a rank's product kernel), 2: the root's separate reduction kernel,
+                            // 3: root, fused (the tail of the root's own product kernel also sums all ranks)
     int nranks, rank;
     u64* slots;             // mailbox slots [MAILBOX_DEPTH][nranks][slot_stride] (the root's memory)
     size_t slot_stride;     // u64 per (epoch, rank) slot
     u64* flags;             // [nranks] last epoch each rank has delivered (the root's memory)
     u64* consumed;          // last epoch the root has summed (the root's memory)
     u64 epoch;              // epoch of this call, or 0: take *epoch_ctr + 1 (device-resident, CUDA-graph friendly)
-    u64* epoch_ctr;         // writer: device-local count of delivered epochs; root: == consumed
+    u64* epoch_ctr;         // device-local count of the epochs this rank has delivered (role 2: == consumed)
     unsigned* counter;      // device-local block-arrival counter (zero between launches)
     int* err;               // set to 1 when a wait times out
+    unsigned long long timeout_ns;  // budget of one wait (a lost peer must not hang the GPU)
 };
 constexpr int MAILBOX_DEPTH = 4;
 

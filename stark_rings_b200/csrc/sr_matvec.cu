@@ -2,13 +2,14 @@
 // (reference: linear_algebra/src/matrix.rs:168-178 with R = RqNTT; the inner product is
 // ntt_form.rs:521-536 (slot-wise Mul) folded with ntt_form.rs:588-601 (Add) from ZERO).
 //
-// The product is independent per CRT slot, so the unit of work is one slot of one column: thread t
-// owns slot (t mod SLOTS) of columns t / SLOTS, t / SLOTS + stride, ...; consecutive threads read
-// consecutive slots, i.e. each warp reads one contiguous span of a row.  Every thread keeps one
-// accumulator per matrix row (RB rows per pass), CTAs reduce per slot index through shared memory
-// and write one partial element per row to scratch; a second small kernel adds the partials mod p
-// in a fixed order, so the result is deterministic.  The same second kernel is the rank-0 modular
-// sum of the multi-GPU commitment (sr_modsum_partials).
+// The product is independent per CRT slot, so the unit of work is one slot of one column.  ONE kernel per pass of
+// up to four matrix rows does everything: every CTA accumulates its share of the columns, reduces per slot index
+// through shared memory and leaves one partial element per row in scratch; the LAST CTA to arrive (a device-wide
+// ticket) adds the partials of all CTAs in a fixed order -- so the result does not depend on which CTA that is --
+// and writes the result rows.  In the column-sharded commitment the same tail stores the rank's partial
+// rows straight into the root rank's mailbox over NVLink and publishes an epoch flag; on the root it then acquires
+// the flags of all ranks and adds their partials mod p.  A commitment is therefore one launch per rank (per four
+// rows), with no separate reduction kernel, no collective call and no host synchronisation.
 #include <cuda_runtime.h>
 
 #define SR_GL_EPS_ON_ALU  // these kernels are bound by the multiply-add pipe: see gl_ring.cuh plus_eps_if
@@ -16,163 +17,185 @@
 #include "bb_ring.cuh"
 #include "gl_ring.cuh"
 #include "sp_ring.cuh"
+#include "sr_launch.cuh"
 #include "sr_slots.cuh"
 #include "sr_tma.cuh"
 
 namespace sr {
 
-// ---- Goldilocks: lazy accumulation ---------------------------------------------------------------
-// sum_j a_j * x_j of 64 x 64 -> 128-bit products is kept UNREDUCED in a 160-bit accumulator held as two
-// interleaved carry-save halves (E: limbs 0..4 takes lo*lo and hi*hi, O: limbs 1..3 takes the two
-// cross products), so that every partial product is one IMAD.WIDE.U32 with carry and no modular
-// reduction happens inside the column loop.  One reduction per thread at the end.
-struct GLAcc {
-    u32 e0, e1, e2, e3, e4, o1, o2, o3;
+// ---- peer-memory primitives ---------------------------------------------------------------------------------------
+SR_D u64 ld_acquire_sys(const u64* p) {
+    u64 v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SR_D void st_release_sys(u64* p, u64 v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+SR_D unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p >= want; false (and *err = 1) when the budget runs out: a lost peer must not hang the GPU
+SR_D bool spin_until(const u64* p, u64 want, int* err, unsigned long long timeout_ns) {
+    if (ld_acquire_sys(p) >= want) return true;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < want) {
+        __nanosleep(100);
+        if (global_ns() - t0 > timeout_ns) {
+            atomicExch(err, 1);
+            return false;
+        }
+    }
+    return true;
+}
+
+// What the tail of a product kernel needs.
+struct MvTail {
+    u64* partial;       // scratch: [gridDim.x][nrows] partial elements
+    u64* out;           // result rows (role 0: nrows elements; role 3: the final sum over all ranks)
+    unsigned* counter;  // arrival ticket, zero between launches
+    int last_pass;      // this launch covers the last rows of the product: publish
+    PeerSync ps;
 };
-SR_D void gl_acc_zero(GLAcc& A) { A.e0 = A.e1 = A.e2 = A.e3 = A.e4 = A.o1 = A.o2 = A.o3 = 0; }
-SR_D void gl_acc_mad(GLAcc& A, u64 a, u64 b) {
-    const u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
-    asm(
-        "mad.lo.cc.u32   %0, %5, %7, %0;\n\t"
-        "madc.hi.cc.u32  %1, %5, %7, %1;\n\t"
-        "madc.lo.cc.u32  %2, %6, %8, %2;\n\t"
-        "madc.hi.cc.u32  %3, %6, %8, %3;\n\t"
-        "addc.u32        %4, %4, 0;\n\t"
-        : "+r"(A.e0), "+r"(A.e1), "+r"(A.e2), "+r"(A.e3), "+r"(A.e4)
-        : "r"(al), "r"(ah), "r"(bl), "r"(bh));
-    asm(
-        "mad.lo.cc.u32   %0, %3, %6, %0;\n\t"
-        "madc.hi.cc.u32  %1, %3, %6, %1;\n\t"
-        "addc.u32        %2, %2, 0;\n\t"
-        "mad.lo.cc.u32   %0, %4, %5, %0;\n\t"
-        "madc.hi.cc.u32  %1, %4, %5, %1;\n\t"
-        "addc.u32        %2, %2, 0;\n\t"
-        : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3)
-        : "r"(al), "r"(ah), "r"(bl), "r"(bh));
-}
-// canonical residue of the accumulated value times 2^POST
-template <int POST>
-SR_D u64 gl_acc_reduce(const GLAcc& A) {
-    // merge: limbs l0..l5 of E + O * 2^32
-    u64 c = (u64)A.e1 + A.o1;
-    const u32 l0 = A.e0, l1 = (u32)c;
-    c = (c >> 32) + (u64)A.e2 + A.o2;
-    const u32 l2 = (u32)c;
-    c = (c >> 32) + (u64)A.e3 + A.o3;
-    const u32 l3 = (u32)c;
-    c = (c >> 32) + (u64)A.e4;
-    const u32 l4 = (u32)c, l5 = (u32)(c >> 32);
-    // 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32, 2^160 = 1 - 2^32 (mod p)
-    u64 r = gl::reduce128((u64)l0 | ((u64)l1 << 32), (u64)l2 | ((u64)l3 << 32));
-    r = gl::sub(r, (u64)l4 << 32);
-    r = gl::add(r, (u64)l5);
-    r = gl::sub(r, (u64)l5 << 32);
-    return gl::canon(POST ? gl::mul_pow2<POST>(r) : r);
-}
 
-#ifndef SR_GLMV_MINB
-#define SR_GLMV_MINB 2
-#endif
-#ifndef SR_GLMV_RB
-#define SR_GLMV_RB 4
-#endif
-constexpr int GLMV_T = 128;
-// Rows [row0, row0 + RB) of the product; same work split and partial layout as matvec_partial_kernel.
-template <int RB>
-__global__ void __launch_bounds__(GLMV_T, SR_GLMV_MINB)
-gl_matvec_lazy_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
-                      const u64* __restrict__ v, u64* __restrict__ partial) {
-    typedef GLSlot S;
-    __shared__ S::Val red[GLMV_T];
-    GLAcc acc[RB][3];
-#pragma unroll
-    for (int r = 0; r < RB; r++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) gl_acc_zero(acc[r][k]);
-    const u64* rp[RB];
-#pragma unroll
-    for (int r = 0; r < RB; r++) rp[r] = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
-
-    const size_t total = ncols * S::SLOTS;
-    const size_t stride = (size_t)gridDim.x * GLMV_T;
-    for (size_t g = (size_t)blockIdx.x * GLMV_T + threadIdx.x; g < total; g += stride) {
-        u64 a[RB][3];
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            a[r][0] = __ldcs(rp[r] + g * 3);
-            a[r][1] = __ldcs(rp[r] + g * 3 + 1);
-            a[r][2] = __ldcs(rp[r] + g * 3 + 2);
-        }
-        const u64 x0 = v[g * 3], x1 = v[g * 3 + 1], x2 = v[g * 3 + 2];
-        const u64 xr1 = gl::mul_pow2<gl::root_exp(1)>(x1), xr2 = gl::mul_pow2<gl::root_exp(1)>(x2);  // u^3 = r
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            gl_acc_mad(acc[r][0], a[r][0], x0);
-            gl_acc_mad(acc[r][0], a[r][1], xr2);
-            gl_acc_mad(acc[r][0], a[r][2], xr1);
-            gl_acc_mad(acc[r][1], a[r][0], x1);
-            gl_acc_mad(acc[r][1], a[r][1], x0);
-            gl_acc_mad(acc[r][1], a[r][2], xr2);
-            gl_acc_mad(acc[r][2], a[r][0], x2);
-            gl_acc_mad(acc[r][2], a[r][1], x1);
-            gl_acc_mad(acc[r][2], a[r][2], x0);
+// ---- the fused tail ---------------------------------------------------------------------------------------------------
+// Called by every thread of the CTA once its partial rows [row0, row0 + rb) are in t.partial.
+// red: shared memory for blockDim.x values; sflag: two shared ints.
+template <class S>
+SR_D void mv_tail(const MvTail& t, size_t nrows, size_t row0, int rb, typename S::Val* red, int* sflag) {
+    typedef typename S::Val Val;
+    const int T = (int)blockDim.x, tid = (int)threadIdx.x;
+    __threadfence();  // this CTA's partials before its ticket
+    __syncthreads();
+    if (tid == 0) sflag[0] = (atomicAdd(t.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!sflag[0]) return;
+    __threadfence();
+    const PeerSync& ps = t.ps;
+    const bool mailbox = (ps.role == 1 || ps.role == 3);
+    u64 epoch = 0;
+    size_t slot0 = 0;
+    u64* dst = t.out;
+    if (mailbox) {
+        epoch = ps.epoch ? ps.epoch : *reinterpret_cast<volatile u64*>(ps.epoch_ctr) + 1;
+        slot0 = (size_t)(epoch % MAILBOX_DEPTH) * ps.nranks;
+        dst = ps.slots + (slot0 + ps.rank) * ps.slot_stride;
+    }
+    // the last thread makes sure the root has summed the epoch that used this mailbox slot before (one peer load,
+    // overlapped with the summation below)
+    if (tid == T - 1) {
+        int ok = 1;
+        if (mailbox && epoch > (u64)MAILBOX_DEPTH)
+            ok = spin_until(ps.consumed, epoch - MAILBOX_DEPTH, ps.err, ps.timeout_ns) ? 1 : 0;
+        sflag[1] = ok;
+    }
+    // sum the gridDim.x partials of every (row, slot) of this pass: SUB threads per unit, each over a strided
+    // subset, then the SUB sums in order.  Fixed order for a given grid: deterministic.
+    const int U = rb * S::SLOTS;
+    int SUB = T / U;
+    if (SUB > 32) SUB = 32;
+    const int G = (int)gridDim.x;
+    if (tid < U * SUB) {
+        const int u = tid / SUB, sub = tid - u * SUB;
+        const int r = u / S::SLOTS, slot = u - r * S::SLOTS;
+        const u64* p = t.partial + (row0 + r) * S::ELEM_U64 + slot * S::SLOT_U64;
+        Val s = S::zero();
+        for (int k = sub; k < G; k += SUB) S::acc(s, S::load_cv(p + (size_t)k * nrows * S::ELEM_U64));
+        red[tid] = s;
+    }
+    __syncthreads();
+    const int ok = sflag[1];
+    if (tid < U * SUB && (tid % SUB) == 0 && ok) {
+        Val s = red[tid];
+        for (int k = 1; k < SUB; k++) S::acc(s, red[tid + k]);
+        const int u = tid / SUB, r = u / S::SLOTS, slot = u - r * S::SLOTS;
+        S::store(dst + (row0 + r) * S::ELEM_U64 + slot * S::SLOT_U64, s);
+    }
+    if (!mailbox) {
+        if (tid == 0) *t.counter = 0;  // ready for the next launch on this stream
+        return;
+    }
+    __threadfence_system();  // the result stores (possibly to peer memory) before the flag
+    __syncthreads();
+    if (tid == 0) {
+        *t.counter = 0;
+        if (t.last_pass && ok) {
+            *ps.epoch_ctr = epoch;
+            __threadfence_system();
+            st_release_sys(ps.flags + ps.rank, epoch);
         }
     }
-#pragma unroll
-    for (int r = 0; r < RB; r++) {
-        if (row0 + r >= nrows) break;
-        S::Val mine;  // Montgomery layout: the product of two raw limbs carries an extra 2^-64 = 2^128
-#pragma unroll
-        for (int k = 0; k < 3; k++) mine.c[k] = gl_acc_reduce<128>(acc[r][k]);
-        red[threadIdx.x] = mine;
-        __syncthreads();
-        if (threadIdx.x < S::SLOTS) {
-            S::Val s = red[threadIdx.x];
-            for (int k = threadIdx.x + S::SLOTS; k < GLMV_T; k += S::SLOTS) S::acc(s, red[k]);
-            S::store(partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, s);
+    if (ps.role != 3 || !t.last_pass) return;
+    // root, fused: wait for every rank's flag (a lane per rank), then out[row] = sum over ranks of their partial rows
+    if (tid == 0) sflag[0] = ok;
+    __syncthreads();
+    for (int r = tid; r < ps.nranks; r += T)
+        if (r != ps.rank && !spin_until(ps.flags + r, epoch, ps.err, ps.timeout_ns)) sflag[0] = 0;
+    __syncthreads();
+    const int all = sflag[0];
+    const u64* slots = ps.slots + slot0 * ps.slot_stride;
+    for (int u = tid; u < (int)nrows * S::SLOTS; u += T) {
+        const size_t off = (size_t)(u / S::SLOTS) * S::ELEM_U64 + (size_t)(u % S::SLOTS) * S::SLOT_U64;
+        if (all) {
+            Val s = S::zero();
+            for (int r = 0; r < ps.nranks; r++) S::acc(s, S::load_cv(slots + (size_t)r * ps.slot_stride + off));
+            S::store(t.out + off, s);
+        } else {
+            S::store_poison(t.out + off);  // not a canonical residue: a timed-out commitment cannot pass for a result
         }
-        __syncthreads();
     }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0 && all) st_release_sys(ps.consumed, epoch);
 }
 
-// TMA-pipelined flavour: the CTA streams chunks of GLTMA_T consecutive slots (3072 B) of v and of RB
-// matrix rows through an NS-deep ring of shared-memory stages filled by 1-D bulk copies
-// (cp.async.bulk + mbarrier complete_tx), so HBM requests are whole 128-byte lines issued far ahead of
-// use and the per-thread 24-byte slot reads hit shared memory (stride 6 words: conflict-free LDS.64).
-constexpr int GLTMA_T = 128, GLTMA_NS = 4;
-// RB rows per launch, split over G thread groups of GLTMA_T threads (RB / G rows per thread): with G = 2
-// a thread carries 6 instead of 12 lazy accumulators (about 110 registers), doubling the resident warps.
-template <int RB, int G>
-__global__ void __launch_bounds__(GLTMA_T * G, 2)
-gl_matvec_tma_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
-                     const u64* __restrict__ v, u64* __restrict__ partial) {
+// ---- Goldilocks -------------------------------------------------------------------------------------------------------
+// Lazy accumulation: sums of 64 x 64 -> 128-bit products are kept UNREDUCED in 160-bit carry-save accumulators
+// (gl::Acc: every partial product is one IMAD.WIDE.U32 with carry, no modular reduction in the column loop).
+// The kernel is bound by the wide multiply-add pipe (ncu, profiles/r01b_gl_ncu.md: fmaheavy 77% busy with nine
+// products per slot and row), so the slot product in F_p[u]/(u^3 - r) is taken the Karatsuba way, with SIX
+// products instead of nine:
+//   P0 = a0 x0, P1 = a1 x1, P2 = a2 x2, P01 = (a0+a1)(x0+x1), P02 = (a0+a2)(x0+x2), P12 = (a1+a2)(x1+x2)
+//   c0 = P0 + r (P12 - P1 - P2),  c1 = (P01 - P0 - P1) + r P2,  c2 = (P02 - P0 - P2) + P1
+// and because the six sums over the columns are linear, the subtractions and the two multiplications by r = 2^40
+// happen ONCE per thread after the column loop.  Per slot, row and column: 24 wide multiply-adds + three modular
+// additions of the row's limbs (the vector's three sums are shared by all rows) instead of 36.
+//
+// Data movement: the CTA streams chunks of CS consecutive slots (CS * 24 bytes) of v and of RB matrix rows through an
+// NS-deep ring of shared-memory stages filled by 1-D bulk copies (cp.async.bulk + mbarrier complete_tx; SASS
+// UBLKCP) issued by a producer warp; RB consumer groups of CS threads (one row each) recycle the stages through
+// per-stage "empty" mbarriers, so there is no CTA barrier in the column loop.  Per-thread 24-byte slot reads from a
+// stage are conflict-free (stride 6 words, LDS.64).
+// (Thread counts are kept at multiples of 128: ptxas sizes the register budget for the thread count rounded up to
+// 128, so a dedicated producer warp on top of 4 x 128 consumers cost 24 registers per thread and spilled.  The
+// copies are issued by thread 0 of the CTA instead, one stage behind the one being consumed.)
+template <int RB, int NS, int CS>
+__global__ void __launch_bounds__(CS * RB, (CS * RB <= 128 ? 4 : (CS * RB <= 256 ? 2 : 1)))
+gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
+                    const u64* __restrict__ v, MvTail tail) {
     typedef GLSlot S;
-    constexpr int CS = GLTMA_T;                  // slots per chunk
-    constexpr int RBT = RB / G;                  // rows per thread
     constexpr uint32_t ROWB = CS * 24;           // bytes per row per stage
-    static_assert(RB % G == 0, "row split");
+    constexpr int STAGE_U64 = (RB + 1) * CS * 3;
     extern __shared__ __align__(128) unsigned char smem[];
     u64* stage = reinterpret_cast<u64*>(smem);   // [NS][RB + 1][CS * 3]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)GLTMA_NS * (RB + 1) * ROWB);
-    __shared__ S::Val red[GLTMA_T];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * (RB + 1) * ROWB);
+    uint64_t* empty = full + NS;
+    int* sflag = reinterpret_cast<int*>(empty + NS);
+    S::Val* red = reinterpret_cast<S::Val*>(smem);  // the stages are dead once the column loop is over
 
-    const int slot = threadIdx.x % CS, grp = threadIdx.x / CS;
+    const int slot = threadIdx.x % CS, grp = threadIdx.x / CS;  // row row0 + grp
     const size_t total = ncols * S::SLOTS;
     const size_t nchunks = (total + CS - 1) / CS;
     const size_t my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < GLTMA_NS; s++) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    auto issue = [&](size_t it) {  // thread 0 only
-        const int s = (int)(it % GLTMA_NS);
-        const size_t chunk = blockIdx.x + it * gridDim.x;
-        const size_t slot0 = chunk * CS;
+    auto issue = [&](size_t it) {  // thread 0 only: chunk `it` of this CTA into stage it % NS
+        const int s = (int)(it % NS);
+        const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
         const uint32_t bytes = (uint32_t)(((total - slot0 < (size_t)CS) ? (total - slot0) : (size_t)CS) * 24);
         mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
-        u64* dst = stage + (size_t)s * (RB + 1) * CS * 3;
+        u64* dst = stage + (size_t)s * STAGE_U64;
         tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
 #pragma unroll
         for (int r = 0; r < RB; r++) {
@@ -180,414 +203,86 @@ gl_matvec_tma_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t r
             tma_load_1d(dst + (size_t)(r + 1) * CS * 3, rp + slot0 * 3, bytes, &full[s]);
         }
     };
-    if (threadIdx.x == 0)
-        for (size_t it = 0; it < (size_t)GLTMA_NS && it < my_chunks; it++) issue(it);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], RB * CS / 32); }
+        mbar_fence_init();
+        for (size_t it = 0; it < (size_t)NS && it < my_chunks; it++) issue(it);
+    }
+    __syncthreads();
 
-    GLAcc acc[RBT][3];
-#pragma unroll
-    for (int r = 0; r < RBT; r++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) gl_acc_zero(acc[r][k]);
+    gl::Acc P0, P1, P2, P01, P02, P12;
+    gl::acc_zero(P0); gl::acc_zero(P1); gl::acc_zero(P2); gl::acc_zero(P01); gl::acc_zero(P02); gl::acc_zero(P12);
 
     for (size_t it = 0; it < my_chunks; it++) {
-        const int s = (int)(it % GLTMA_NS);
-        mbar_wait(&full[s], (uint32_t)((it / GLTMA_NS) & 1));
+        const int s = (int)(it % NS);
+        if (threadIdx.x == 0 && it > 0 && it - 1 + NS < my_chunks) {
+            // refill the stage that was consumed one trip ago (every warp has arrived on its `empty` barrier by now,
+            // or is about to: no CTA barrier, and the other warps never wait for this one)
+            mbar_wait(&empty[(it - 1) % NS], (uint32_t)(((it - 1) / NS) & 1));
+            issue(it - 1 + NS);
+        }
+        __syncwarp();
+        mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
         const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
         const bool live = slot0 + slot < total;
-        const u64* base = stage + (size_t)s * (RB + 1) * CS * 3 + slot * 3;
-        u64 x0 = 0, x1 = 0, x2 = 0, a[RBT][3];
-        if (live) { x0 = base[0]; x1 = base[1]; x2 = base[2]; }
-#pragma unroll
-        for (int r = 0; r < RBT; r++) {
-            const u64* q = base + (size_t)(grp * RBT + r + 1) * CS * 3;
-            a[r][0] = live ? q[0] : 0; a[r][1] = live ? q[1] : 0; a[r][2] = live ? q[2] : 0;
-        }
-        __syncthreads();  // every thread has read stage s: it can be refilled
-        if (threadIdx.x == 0 && it + GLTMA_NS < my_chunks) issue(it + GLTMA_NS);
-        const u64 xr1 = gl::mul_pow2<gl::root_exp(1)>(x1), xr2 = gl::mul_pow2<gl::root_exp(1)>(x2);
-#pragma unroll
-        for (int r = 0; r < RBT; r++) {
-            gl_acc_mad(acc[r][0], a[r][0], x0);
-            gl_acc_mad(acc[r][0], a[r][1], xr2);
-            gl_acc_mad(acc[r][0], a[r][2], xr1);
-            gl_acc_mad(acc[r][1], a[r][0], x1);
-            gl_acc_mad(acc[r][1], a[r][1], x0);
-            gl_acc_mad(acc[r][1], a[r][2], xr2);
-            gl_acc_mad(acc[r][2], a[r][0], x2);
-            gl_acc_mad(acc[r][2], a[r][1], x1);
-            gl_acc_mad(acc[r][2], a[r][2], x0);
-        }
+        const u64* bx = stage + (size_t)s * STAGE_U64 + slot * 3;
+        const u64* ba = bx + (size_t)(grp + 1) * CS * 3;
+        u64 x0 = 0, x1 = 0, x2 = 0, a0 = 0, a1 = 0, a2 = 0;
+        if (live) { x0 = bx[0]; x1 = bx[1]; x2 = bx[2]; a0 = ba[0]; a1 = ba[1]; a2 = ba[2]; }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+        // limbs in memory are canonical, so the weak-form additions are exact residues (a + b with b canonical)
+        const u64 x01 = gl::add(x0, x1), x02 = gl::add(x0, x2), x12 = gl::add(x1, x2);
+        const u64 a01 = gl::add(a0, a1), a02 = gl::add(a0, a2), a12 = gl::add(a1, a2);
+        gl::acc_mad(P0, a0, x0);
+        gl::acc_mad(P1, a1, x1);
+        gl::acc_mad(P2, a2, x2);
+        gl::acc_mad(P01, a01, x01);
+        gl::acc_mad(P02, a02, x02);
+        gl::acc_mad(P12, a12, x12);
     }
-#pragma unroll
-    for (int r = 0; r < RB; r++) {
-        if (row0 + r >= nrows) break;
-        if (grp == r / RBT) {
-            S::Val mine;
-#pragma unroll
-            for (int k = 0; k < 3; k++) mine.c[k] = gl_acc_reduce<128>(acc[r % RBT][k]);
-            red[slot] = mine;
-        }
-        __syncthreads();
-        if (threadIdx.x < S::SLOTS) {
-            S::Val sacc = red[threadIdx.x];
-            for (int k = threadIdx.x + S::SLOTS; k < GLTMA_T; k += S::SLOTS) S::acc(sacc, red[k]);
-            S::store(partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, sacc);
-        }
-        __syncthreads();
-    }
-}
-
-// Warp-specialised flavour: one producer warp (lane 0 issues the bulk copies) plus GLTMA_T consumer threads.
-// Stages are recycled through per-stage "empty" mbarriers (one arrival per consumer warp), so there is no
-// CTA barrier in the column loop and the consumer warps run up to NS stages apart.
-template <int RB>
-__global__ void __launch_bounds__(GLTMA_T + 32, 2)
-gl_matvec_ws_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
-                    const u64* __restrict__ v, u64* __restrict__ partial) {
-    typedef GLSlot S;
-    constexpr int CS = GLTMA_T, NS = GLTMA_NS;
-    constexpr uint32_t ROWB = CS * 24;
-    extern __shared__ __align__(128) unsigned char smem[];
-    u64* stage = reinterpret_cast<u64*>(smem);   // [NS][RB + 1][CS * 3]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * (RB + 1) * ROWB);
-    uint64_t* empty = full + NS;
-    __shared__ S::Val red[GLTMA_T];
-
-    const bool producer = threadIdx.x >= CS;
-    const int slot = threadIdx.x;  // consumers only
-    const size_t total = ncols * S::SLOTS;
-    const size_t nchunks = (total + CS - 1) / CS;
-    const size_t my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CS / 32); }
-        mbar_fence_init();
+    __syncthreads();  // every stage has been consumed: `red` may overwrite them
+    {
+        const u64 p0 = gl::acc_reduce(P0), p1 = gl::acc_reduce(P1), p2 = gl::acc_reduce(P2);
+        const u64 p01 = gl::acc_reduce(P01), p02 = gl::acc_reduce(P02), p12 = gl::acc_reduce(P12);
+        constexpr int E = gl::root_exp(1);  // u^3 = r = 2^40
+        const u64 c0 = gl::add(gl::mul_pow2<E>(gl::sub(gl::sub(p12, p1), p2)), p0);
+        const u64 c1 = gl::add(gl::sub(gl::sub(p01, p0), p1), gl::canon(gl::mul_pow2<E>(p2)));
+        const u64 c2 = gl::add(gl::sub(gl::sub(p02, p0), p2), p1);
+        S::Val mine;  // Montgomery layout: the product of two raw limbs carries an extra 2^-64 = 2^128
+        mine.c[0] = gl::canon(gl::mul_pow2<128>(c0));
+        mine.c[1] = gl::canon(gl::mul_pow2<128>(c1));
+        mine.c[2] = gl::canon(gl::mul_pow2<128>(c2));
+        red[threadIdx.x] = mine;
     }
     __syncthreads();
-
-    GLAcc acc[RB][3];
-#pragma unroll
-    for (int r = 0; r < RB; r++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) gl_acc_zero(acc[r][k]);
-
-    if (producer) {
-        if (threadIdx.x == CS) {
-            for (size_t it = 0; it < my_chunks; it++) {
-                const int s = (int)(it % NS);
-                if (it >= (size_t)NS) mbar_wait(&empty[s], (uint32_t)(((it / NS) - 1) & 1));
-                const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
-                const uint32_t bytes = (uint32_t)(((total - slot0 < (size_t)CS) ? (total - slot0) : (size_t)CS) * 24);
-                mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
-                u64* dst = stage + (size_t)s * (RB + 1) * CS * 3;
-                tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
-#pragma unroll
-                for (int r = 0; r < RB; r++) {
-                    const u64* rp = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
-                    tma_load_1d(dst + (size_t)(r + 1) * CS * 3, rp + slot0 * 3, bytes, &full[s]);
-                }
-            }
-        }
-    } else {
-        for (size_t it = 0; it < my_chunks; it++) {
-            const int s = (int)(it % NS);
-            mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
-            const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
-            const bool live = slot0 + slot < total;
-            const u64* base = stage + (size_t)s * (RB + 1) * CS * 3 + slot * 3;
-            u64 x0 = 0, x1 = 0, x2 = 0, a[RB][3];
-            if (live) { x0 = base[0]; x1 = base[1]; x2 = base[2]; }
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                const u64* q = base + (size_t)(r + 1) * CS * 3;
-                a[r][0] = live ? q[0] : 0; a[r][1] = live ? q[1] : 0; a[r][2] = live ? q[2] : 0;
-            }
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
-            const u64 xr1 = gl::mul_pow2<gl::root_exp(1)>(x1), xr2 = gl::mul_pow2<gl::root_exp(1)>(x2);
-#pragma unroll
-            for (int r = 0; r < RB; r++) {
-                gl_acc_mad(acc[r][0], a[r][0], x0);
-                gl_acc_mad(acc[r][0], a[r][1], xr2);
-                gl_acc_mad(acc[r][0], a[r][2], xr1);
-                gl_acc_mad(acc[r][1], a[r][0], x1);
-                gl_acc_mad(acc[r][1], a[r][1], x0);
-                gl_acc_mad(acc[r][1], a[r][2], xr2);
-                gl_acc_mad(acc[r][2], a[r][0], x2);
-                gl_acc_mad(acc[r][2], a[r][1], x1);
-                gl_acc_mad(acc[r][2], a[r][2], x0);
-            }
-        }
+    if (threadIdx.x < RB * S::SLOTS) {  // thread (r, s8): CTA sum of slot index s8 of row r, fixed order
+        const int r = threadIdx.x / S::SLOTS, s8 = threadIdx.x % S::SLOTS;
+        S::Val sacc = red[r * CS + s8];
+        for (int k = s8 + S::SLOTS; k < CS; k += S::SLOTS) S::acc(sacc, red[r * CS + k]);
+        if (row0 + r < nrows)
+            S::store(tail.partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + s8 * S::SLOT_U64, sacc);
     }
-#pragma unroll
-    for (int r = 0; r < RB; r++) {
-        if (row0 + r >= nrows) break;
-        if (!producer) {
-            S::Val mine;
-#pragma unroll
-            for (int k = 0; k < 3; k++) mine.c[k] = gl_acc_reduce<128>(acc[r][k]);
-            red[slot] = mine;
-        }
-        __syncthreads();
-        if (threadIdx.x < S::SLOTS) {
-            S::Val sacc = red[threadIdx.x];
-            for (int k = threadIdx.x + S::SLOTS; k < GLTMA_T; k += S::SLOTS) S::acc(sacc, red[k]);
-            S::store(partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, sacc);
-        }
-        __syncthreads();
-    }
-}
-
-// The same with the rows split over G consumer groups (as gl_matvec_tma_kernel): no CTA barrier in the column loop.
-template <int RB, int G>
-__global__ void __launch_bounds__(GLTMA_T * G + 32, 2)
-gl_matvec_wsg_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
-                    const u64* __restrict__ v, u64* __restrict__ partial) {
-    typedef GLSlot S;
-    constexpr int CS = GLTMA_T, NS = GLTMA_NS, RBT = RB / G;
-    static_assert(RB % G == 0, "row split");
-    constexpr uint32_t ROWB = CS * 24;
-    extern __shared__ __align__(128) unsigned char smem[];
-    u64* stage = reinterpret_cast<u64*>(smem);   // [NS][RB + 1][CS * 3]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * (RB + 1) * ROWB);
-    uint64_t* empty = full + NS;
-    __shared__ S::Val red[GLTMA_T];
-
-    const bool producer = threadIdx.x >= CS * G;
-    const int slot = threadIdx.x % CS, grp = threadIdx.x / CS;  // consumers only
-    const size_t total = ncols * S::SLOTS;
-    const size_t nchunks = (total + CS - 1) / CS;
-    const size_t my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], G * CS / 32); }
-        mbar_fence_init();
-    }
+    const int rb = (nrows - row0 < (size_t)RB) ? (int)(nrows - row0) : RB;
     __syncthreads();
-
-    GLAcc acc[RBT][3];
-#pragma unroll
-    for (int r = 0; r < RBT; r++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) gl_acc_zero(acc[r][k]);
-
-    if (producer) {
-        if (threadIdx.x == CS * G) {
-            for (size_t it = 0; it < my_chunks; it++) {
-                const int s = (int)(it % NS);
-                if (it >= (size_t)NS) mbar_wait(&empty[s], (uint32_t)(((it / NS) - 1) & 1));
-                const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
-                const uint32_t bytes = (uint32_t)(((total - slot0 < (size_t)CS) ? (total - slot0) : (size_t)CS) * 24);
-                mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
-                u64* dst = stage + (size_t)s * (RB + 1) * CS * 3;
-                tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
-#pragma unroll
-                for (int r = 0; r < RB; r++) {
-                    const u64* rp = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
-                    tma_load_1d(dst + (size_t)(r + 1) * CS * 3, rp + slot0 * 3, bytes, &full[s]);
-                }
-            }
-        }
-    } else {
-        for (size_t it = 0; it < my_chunks; it++) {
-            const int s = (int)(it % NS);
-            mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
-            const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
-            const bool live = slot0 + slot < total;
-            const u64* base = stage + (size_t)s * (RB + 1) * CS * 3 + slot * 3;
-            u64 x0 = 0, x1 = 0, x2 = 0, a[RBT][3];
-            if (live) { x0 = base[0]; x1 = base[1]; x2 = base[2]; }
-#pragma unroll
-            for (int r = 0; r < RBT; r++) {
-                const u64* q = base + (size_t)(grp * RBT + r + 1) * CS * 3;
-                a[r][0] = live ? q[0] : 0; a[r][1] = live ? q[1] : 0; a[r][2] = live ? q[2] : 0;
-            }
-            __syncwarp();
-            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
-            const u64 xr1 = gl::mul_pow2<gl::root_exp(1)>(x1), xr2 = gl::mul_pow2<gl::root_exp(1)>(x2);
-#pragma unroll
-            for (int r = 0; r < RBT; r++) {
-                gl_acc_mad(acc[r][0], a[r][0], x0);
-                gl_acc_mad(acc[r][0], a[r][1], xr2);
-                gl_acc_mad(acc[r][0], a[r][2], xr1);
-                gl_acc_mad(acc[r][1], a[r][0], x1);
-                gl_acc_mad(acc[r][1], a[r][1], x0);
-                gl_acc_mad(acc[r][1], a[r][2], xr2);
-                gl_acc_mad(acc[r][2], a[r][0], x2);
-                gl_acc_mad(acc[r][2], a[r][1], x1);
-                gl_acc_mad(acc[r][2], a[r][2], x0);
-            }
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < RB; r++) {
-        if (row0 + r >= nrows) break;
-        if (!producer && grp == r / RBT) {
-            S::Val mine;
-#pragma unroll
-            for (int k = 0; k < 3; k++) mine.c[k] = gl_acc_reduce<128>(acc[r % RBT][k]);
-            red[slot] = mine;
-        }
-        __syncthreads();
-        if (threadIdx.x < S::SLOTS) {
-            S::Val sacc = red[threadIdx.x];
-            for (int k = threadIdx.x + S::SLOTS; k < GLTMA_T; k += S::SLOTS) S::acc(sacc, red[k]);
-            S::store(partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, sacc);
-        }
-        __syncthreads();
-    }
+    mv_tail<S>(tail, nrows, row0, rb, red, sflag);
 }
 
-#ifndef SR_GLMV_G
-#define SR_GLMV_G 2
-#endif
-// 4-row passes: warp-specialised row-split kernel (no CTA barrier in the column loop) unless -DSR_GLMV_CTASYNC:
-// 0.582 vs 0.567 of the HBM roofline at m = 2^20, 0.652 vs 0.628 at 2^22 (kappa = 4)
-#if !defined(SR_GLMV_CTASYNC) && !defined(SR_GLMV_WSG)
-#define SR_GLMV_WSG
-#endif
-template <int RB>
-static cudaError_t gl_tma_launch_rb(int grid, const u64* const* d_rows, size_t nrows, size_t row0, size_t ncols,
-                                    const u64* v, u64* parts, cudaStream_t st) {
-    // RB < 4: warp-specialised producer/consumer kernel (kappa = 1: 0.100 vs 0.157 ms at m = 2^20);
-    // RB = 4: the row-split kernel (the 12-accumulator consumer would spill under the 168-register cap).
-    constexpr bool WS = (RB < 4);
-    constexpr int G = WS ? 1 : SR_GLMV_G;
-#if defined(SR_GLMV_WSG)
-    void (*kern)(const u64* const*, size_t, size_t, size_t, const u64*, u64*) =
-        WS ? (void (*)(const u64* const*, size_t, size_t, size_t, const u64*, u64*))gl_matvec_ws_kernel<(RB < 4 ? RB : 1)>
-           : (void (*)(const u64* const*, size_t, size_t, size_t, const u64*, u64*))gl_matvec_wsg_kernel<RB, (RB >= 4 ? SR_GLMV_G : 1)>;
-    const int threads = WS ? GLTMA_T + 32 : GLTMA_T * G + 32;
-#else
-    void (*kern)(const u64* const*, size_t, size_t, size_t, const u64*, u64*) =
-        WS ? (void (*)(const u64* const*, size_t, size_t, size_t, const u64*, u64*))gl_matvec_ws_kernel<(RB < 4 ? RB : 1)>
-           : (void (*)(const u64* const*, size_t, size_t, size_t, const u64*, u64*))gl_matvec_tma_kernel<RB, (RB >= 4 ? SR_GLMV_G : 1)>;
-    const int threads = WS ? GLTMA_T + 32 : GLTMA_T * G;
-#endif
-    const size_t smem = (size_t)GLTMA_NS * (RB + 1) * GLTMA_T * 24 + 2 * GLTMA_NS * sizeof(uint64_t);
-    static thread_local bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    kern<<<grid, threads, smem, st>>>(d_rows, nrows, row0, ncols, v, parts);
-    return cudaGetLastError();
-}
-
-// Three threads per slot: the nine products of a slot product fall on five diagonals
-//   d0 = a0 x0, d1 = a0 x1 + a1 x0, d2 = a0 x2 + a1 x1 + a2 x0, d3 = a1 x2 + a2 x1, d4 = a2 x2,
-//   c0 = d0 + r d3, c1 = d1 + r d4, c2 = d2   (u^3 = r = 2^40),
-// and are split 3 + 3 + 3 over the threads (part 0: d0 | d3, part 1: d4 | d1, part 2: a0 x2 | a1 x1 + a2 x0),
-// each thread keeping two lazy accumulators per matrix row.  No multiplication by r and no reduction
-// inside the column loop; operand indices are per-lane constants, so all lanes run one instruction
-// stream.  ~100 registers -> 18 warps per SM instead of 8.
-#ifndef SR_GL3_MINB
-#define SR_GL3_MINB 2
-#endif
-constexpr int GL3_SLOTS = 64, GL3_T = 3 * GL3_SLOTS, GL3_NS = 4;
-template <int RB>
-__global__ void __launch_bounds__(GL3_T, SR_GL3_MINB)
-gl_matvec_tma3_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
-                      const u64* __restrict__ v, u64* __restrict__ partial) {
-    typedef GLSlot S;
-    constexpr int CS = GL3_SLOTS;
-    constexpr uint32_t ROWB = CS * 24;
-    extern __shared__ __align__(128) unsigned char smem[];
-    u64* stage = reinterpret_cast<u64*>(smem);   // [NS][RB + 1][CS * 3]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)GL3_NS * (RB + 1) * ROWB);
-    __shared__ u64 red[GL3_SLOTS][3];
-
-    const int slot = threadIdx.x / 3, part = threadIdx.x - 3 * slot;
-    // operand indices: accA += a[ia] x[ja];  accB += a[ib1] x[jb1] + a[ib2] x[jb2]
-    const int ia = (part == 1) ? 2 : 0, ja = (part == 0) ? 0 : 2;
-    const int ib1 = (part == 1) ? 0 : 1, jb1 = (part == 0) ? 2 : 1;
-    const int ib2 = (part == 1) ? 1 : 2, jb2 = (part == 0) ? 1 : 0;
-
-    const u64* rp[RB];
-#pragma unroll
-    for (int r = 0; r < RB; r++) rp[r] = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
-    const size_t total = ncols * S::SLOTS;
-    const size_t nchunks = (total + CS - 1) / CS;
-    const size_t my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < GL3_NS; s++) mbar_init(&full[s], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    auto issue = [&](size_t it) {
-        const int s = (int)(it % GL3_NS);
-        const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
-        const uint32_t bytes = (uint32_t)(((total - slot0 < (size_t)CS) ? (total - slot0) : (size_t)CS) * 24);
-        mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
-        u64* dst = stage + (size_t)s * (RB + 1) * CS * 3;
-        tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
-#pragma unroll
-        for (int r = 0; r < RB; r++) tma_load_1d(dst + (size_t)(r + 1) * CS * 3, rp[r] + slot0 * 3, bytes, &full[s]);
-    };
-    if (threadIdx.x == 0)
-        for (size_t it = 0; it < (size_t)GL3_NS && it < my_chunks; it++) issue(it);
-
-    GLAcc accA[RB], accB[RB];
-#pragma unroll
-    for (int r = 0; r < RB; r++) { gl_acc_zero(accA[r]); gl_acc_zero(accB[r]); }
-
-    for (size_t it = 0; it < my_chunks; it++) {
-        const int s = (int)(it % GL3_NS);
-        mbar_wait(&full[s], (uint32_t)((it / GL3_NS) & 1));
-        const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
-        const bool live = slot0 + slot < total;
-        const u64* base = stage + (size_t)s * (RB + 1) * CS * 3 + slot * 3;
-        u64 xa = 0, xb1 = 0, xb2 = 0, aa[RB], ab1[RB], ab2[RB];
-        if (live) { xa = base[ja]; xb1 = base[jb1]; xb2 = base[jb2]; }
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            const u64* q = base + (size_t)(r + 1) * CS * 3;
-            aa[r] = live ? q[ia] : 0; ab1[r] = live ? q[ib1] : 0; ab2[r] = live ? q[ib2] : 0;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0 && it + GL3_NS < my_chunks) issue(it + GL3_NS);
-#pragma unroll
-        for (int r = 0; r < RB; r++) {
-            gl_acc_mad(accA[r], aa[r], xa);
-            gl_acc_mad(accB[r], ab1[r], xb1);
-            gl_acc_mad(accB[r], ab2[r], xb2);
-        }
-    }
-    // thread -> one coefficient of the slot: part 0: c0 = A + r B, part 1: c1 = B + r A, part 2: c2 = A + B
-#pragma unroll
-    for (int r = 0; r < RB; r++) {
-        if (row0 + r >= nrows) break;
-        const u64 ra = gl_acc_reduce<0>(accA[r]), rb = gl_acc_reduce<0>(accB[r]);
-        u64 c;
-        if (part == 0) c = gl::add(gl::mul_pow2<gl::root_exp(1)>(rb), ra);
-        else if (part == 1) c = gl::add(gl::mul_pow2<gl::root_exp(1)>(ra), rb);
-        else c = gl::add(ra, rb);
-        red[slot][part] = gl::canon(gl::mul_pow2<128>(c));  // Montgomery layout: extra 2^-64 = 2^128
-        __syncthreads();
-        if (threadIdx.x < S::SLOTS * 3) {  // 24 threads: (slot index s8, coefficient k)
-            const int s8 = threadIdx.x / 3, k = threadIdx.x - 3 * s8;
-            u64 acc = 0;
-            for (int q = s8; q < GL3_SLOTS; q += S::SLOTS) acc = gl::add(acc, red[q][k]);
-            partial[((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + s8 * 3 + k] = gl::canon(acc);
-        }
-        __syncthreads();
-    }
-}
-
-template <int RB>
-static cudaError_t gl_tma3_launch_rb(int grid, const u64* const* d_rows, size_t nrows, size_t row0, size_t ncols,
-                                     const u64* v, u64* parts, cudaStream_t st) {
-    auto kern = gl_matvec_tma3_kernel<RB>;
-    const size_t smem = (size_t)GL3_NS * (RB + 1) * GL3_SLOTS * 24 + GL3_NS * sizeof(uint64_t);
-    static thread_local bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    kern<<<grid, GL3_T, smem, st>>>(d_rows, nrows, row0, ncols, v, parts);
+template <int RB, int NS, int CS>
+static cudaError_t gl_k6_launch(const u64* const* d_rows, size_t nrows, size_t row0, size_t ncols, const u64* v,
+                                const MvTail& tail, int max_grid, cudaStream_t st, int sms) {
+    auto kern = gl_matvec_k6_kernel<RB, NS, CS>;
+    const int threads = CS * RB;
+    const size_t smem = (size_t)NS * (RB + 1) * CS * 24 + 2 * NS * sizeof(uint64_t) + 16;
+    static KernelCache cache;
+    int bps = 0;
+    cudaError_t e = cache.configure(kern, threads, smem, &bps);
+    if (e != cudaSuccess) return e;
+    const size_t nchunks = (ncols * GLSlot::SLOTS + CS - 1) / CS;
+    size_t grid = (size_t)sms * bps;
+    if (grid > (size_t)max_grid) grid = max_grid;
+    if (grid > nchunks) grid = nchunks;
+    kern<<<(unsigned)grid, threads, smem, st>>>(d_rows, nrows, row0, ncols, v, tail);
     return cudaGetLastError();
 }
 
@@ -599,12 +294,16 @@ static cudaError_t gl_tma3_launch_rb(int grid, const u64* const* d_rows, size_t 
 #endif
 constexpr int MV_T = SR_MV_T;  // threads per CTA (multiple of every SLOTS)
 
-// partial[(blockIdx * nrows + row) * ELEM + slot*SLOT_U64 ...] = CTA-local sum for rows [row0, row0+RB)
+// BabyBear / Starknet prime: thread t owns slot (t mod SLOTS) of columns t / SLOTS, t / SLOTS + stride, ...;
+// consecutive threads read consecutive slots, i.e. each warp reads one contiguous span of a row.  Every thread keeps
+// one accumulator per matrix row (RB rows per pass).  Linear factors of the slot product are applied once per
+// accumulated sum instead of per product (S::mul_lazy / S::finish).
 template <class S, int RB>
 __global__ void __launch_bounds__(MV_T)
 matvec_partial_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
-                      const u64* __restrict__ v, u64* __restrict__ partial) {
+                      const u64* __restrict__ v, MvTail tail) {
     __shared__ typename S::Val red[MV_T];
+    __shared__ int sflag[2];
     typename S::Val acc[RB];
 #pragma unroll
     for (int r = 0; r < RB; r++) acc[r] = S::zero();
@@ -634,78 +333,42 @@ matvec_partial_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t 
         if (threadIdx.x < S::SLOTS) {
             typename S::Val s = red[threadIdx.x];
             for (int k = threadIdx.x + S::SLOTS; k < MV_T; k += S::SLOTS) S::acc(s, red[k]);
-            S::store(partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, s);
+            S::store(tail.partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, s);
         }
         __syncthreads();
     }
+    const int rb = (nrows - row0 < (size_t)RB) ? (int)(nrows - row0) : RB;
+    mv_tail<S>(tail, nrows, row0, rb, red, sflag);
 }
 
-// ---- NVLink peer-memory hand-off of the column-sharded commitment -----------------------------------
-// The last kernel of a rank's partial product writes its nrows partial elements STRAIGHT into the root rank's
-// mailbox (peer memory mapped through CUDA IPC; plain stores travel over NVLink), then publishes an epoch flag
-// with release semantics at system scope.  The root's reduction kernel acquires the flags of all ranks and adds the
-// partials mod p.  No NCCL call, no host synchronisation, no extra launch: the exchange is fused into the two
-// kernels that produce and consume the data.  Slots are reused every MAILBOX_DEPTH epochs; a writer first checks
-// the root's `consumed` counter (peer load) so that it never overruns a slot the root has not summed yet.
-SR_D u64 ld_acquire_sys(const u64* p) {
-    u64 v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-SR_D void st_release_sys(u64* p, u64 v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-SR_D unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-constexpr unsigned long long PEER_TIMEOUT_NS = 4000000000ull;  // a lost peer must not hang the GPU: flag an error
-// spin until *p >= want; false (and *err = 1) on timeout
-SR_D bool spin_until(const u64* p, u64 want, int* err) {
-    if (ld_acquire_sys(p) >= want) return true;
-    const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(p) < want) {
-        __nanosleep(200);
-        if (global_ns() - t0 > PEER_TIMEOUT_NS) {
-            atomicExch(err, 1);
-            return false;
-        }
-    }
-    return true;
-}
-// out[row] = sum_k parts[(k * stride_rows + row)]  (k < nparts).  One CTA per (row, slot), fixed-order tree: deterministic.
-// (A warp per (row, slot) took 10.6 us for the 296 partials of a kappa = 4 commit, a quarter of the per-rank time at
-// 8 GPUs: 32 warps on the whole GPU, each chaining ten dependent loads.)
-// ps.role 1 (writer): `out` is replaced by this rank's mailbox slot of the epoch; the kernel first makes sure the
-// root has summed the epoch that used the slot before, and publishes the epoch flag once every block has stored.
-// ps.role 2 (root): `parts` is replaced by the epoch's nranks slots; the kernel first acquires all rank flags and
-// publishes `consumed` at the end.
+// ---- stand-alone modular sum of partial rows ---------------------------------------------------------------------------
+// out[row] = sum_k parts[(k * stride_rows + row)]  (k < nparts).  One CTA per (row, slot), fixed-order tree:
+// deterministic.  This is sr_modsum_partials (the rank-0 sum behind an NCCL all-gather) and, with ps.role 2, the
+// root's separate mailbox reduction (sr_commit_reduce): `parts` is replaced by the epoch's nranks slots; the kernel
+// first acquires all rank flags and publishes `consumed` at the end.
 template <class S>
 __global__ void __launch_bounds__(128)
 sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t stride_rows, size_t nrows,
                     u64* __restrict__ out, PeerSync ps) {
     __shared__ typename S::Val red[128];
+    __shared__ int sok;
     u64 epoch = 0;
-    if (ps.role != 0) {  // uniform per launch
+    int ok = 1;
+    if (ps.role == 2) {  // uniform per launch
         epoch = ps.epoch ? ps.epoch : *reinterpret_cast<volatile u64*>(ps.epoch_ctr) + 1;
-        const size_t slot0 = (size_t)(epoch % MAILBOX_DEPTH) * ps.nranks;
-        if (ps.role == 1) {
-            out = ps.slots + (slot0 + ps.rank) * ps.slot_stride;
-            if (threadIdx.x == 0 && epoch > (u64)MAILBOX_DEPTH) spin_until(ps.consumed, epoch - MAILBOX_DEPTH, ps.err);
-        } else {
-            parts = ps.slots + slot0 * ps.slot_stride;
-            for (int r = threadIdx.x; r < ps.nranks; r += 128) spin_until(ps.flags + r, epoch, ps.err);  // a lane per rank
-        }
+        parts = ps.slots + (size_t)(epoch % MAILBOX_DEPTH) * ps.nranks * ps.slot_stride;
+        if (threadIdx.x == 0) sok = 1;
         __syncthreads();
+        for (int r = threadIdx.x; r < ps.nranks; r += 128)  // a lane per rank
+            if (!spin_until(ps.flags + r, epoch, ps.err, ps.timeout_ns)) sok = 0;
+        __syncthreads();
+        ok = sok;
     }
-    // one CTA per (row, slot): the 128 threads stride over the partials (independent loads, two or three each for the
-    // 296 partials of a mat-vec), then a shared-memory tree adds the 128 thread sums in a fixed order
     const size_t idx = blockIdx.x;  // (row, slot)
     const size_t row = idx / S::SLOTS, slot = idx % S::SLOTS;
     typename S::Val s = S::zero();
     for (size_t k = threadIdx.x; k < nparts; k += 128)
-        S::acc(s, S::load(parts + (k * stride_rows + row) * S::ELEM_U64 + slot * S::SLOT_U64));
+        S::acc(s, S::load_cv(parts + (k * stride_rows + row) * S::ELEM_U64 + slot * S::SLOT_U64));
     red[threadIdx.x] = s;
     __syncthreads();
 #pragma unroll
@@ -717,19 +380,18 @@ sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t stride_
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, red[0]);
-    if (ps.role != 0) {
+    if (threadIdx.x == 0) {
+        if (ok) S::store(out + row * S::ELEM_U64 + slot * S::SLOT_U64, red[0]);
+        else S::store_poison(out + row * S::ELEM_U64 + slot * S::SLOT_U64);
+    }
+    if (ps.role == 2) {
         // every block has read the epoch counter before the last one arrives, so it may be advanced here
-        u64* flag = ps.role == 1 ? ps.flags + ps.rank : ps.consumed;
-        __threadfence_system();  // this thread's stores (possibly to peer memory) before the arrival
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned arrived = atomicAdd(ps.counter, 1u);
             if (arrived == gridDim.x - 1) {
                 *ps.counter = 0;  // ready for the next launch on this stream
-                if (ps.role == 1) *ps.epoch_ctr = epoch;
-                __threadfence_system();
-                st_release_sys(flag, epoch);
+                if (ok) st_release_sys(ps.consumed, epoch);
             }
         }
     }
@@ -737,114 +399,80 @@ sum_partials_kernel(const u64* __restrict__ parts, size_t nparts, size_t stride_
 
 static int mv_grid(int sms) { return sms * 4; }
 
-template <class S>
-static cudaError_t final_sum(const u64* parts, size_t nparts, size_t nrows, u64* out, const PeerSync& ps,
-                             cudaStream_t st) {
-    const size_t n = nrows * S::SLOTS;
-    sum_partials_kernel<S><<<(unsigned)n, 128, 0, st>>>(parts, nparts, nrows, nrows, out, ps);
-    return cudaGetLastError();
-}
-
-static cudaError_t gl_matvec_launch(const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v, u64* out,
-                                    void* scratch, cudaStream_t st, int sms, int* launches, const PeerSync& ps) {
-    typedef GLSlot S;
-    *launches = 0;
-    if (nrows == 0) return cudaSuccess;
-    if (ncols == 0) {  // Sum of nothing = ZERO (a sum over zero partials, so that a mailbox flag is still published)
-        (*launches)++;
-        return final_sum<S>(reinterpret_cast<u64*>(scratch), 0, nrows, out, ps, st);
-    }
-    size_t total = ncols * S::SLOTS;
-    int grid = mv_grid(sms);  // scratch is sized for mv_grid(sms) partials
-    size_t need = (total + GLMV_T - 1) / GLMV_T;
-    if ((size_t)grid > need) grid = (int)need;
-    u64* parts = reinterpret_cast<u64*>(scratch);
-    size_t row0 = 0;
-#if defined(SR_GLMV_TMA3)
-    {
-        int g2 = sms * SR_GL3_MINB;
-        const size_t nchunks = (total + GL3_SLOTS - 1) / GL3_SLOTS;
-        if ((size_t)g2 > nchunks) g2 = (int)nchunks;
-        while (row0 < nrows) {
-            const size_t left = nrows - row0;
-            cudaError_t e;
-            if (left >= 4) { e = gl_tma3_launch_rb<4>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 4; }
-            else if (left >= 2) { e = gl_tma3_launch_rb<2>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 2; }
-            else { e = gl_tma3_launch_rb<1>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 1; }
-            if (e != cudaSuccess) return e;
-            (*launches)++;
-        }
-        grid = g2;
-    }
-#elif !defined(SR_GLMV_NO_TMA)
-    {
-        int g2 = sms * 2;  // two resident CTAs per SM
-        const size_t nchunks = (total + GLTMA_T - 1) / GLTMA_T;
-        if ((size_t)g2 > nchunks) g2 = (int)nchunks;
-        while (row0 < nrows) {
-            const size_t left = nrows - row0;
-            cudaError_t e;
-            if (left >= 4) { e = gl_tma_launch_rb<4>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 4; }
-            else if (left >= 2) { e = gl_tma_launch_rb<2>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 2; }
-            else { e = gl_tma_launch_rb<1>(g2, d_rows, nrows, row0, ncols, v, parts, st); row0 += 1; }
-            if (e != cudaSuccess) return e;
-            (*launches)++;
-        }
-        grid = g2;
-    }
-#endif
-    while (row0 < nrows) {
-        const size_t left = nrows - row0;
-        if (left >= 4 && SR_GLMV_RB >= 4) { gl_matvec_lazy_kernel<4><<<grid, GLMV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, parts); row0 += 4; }
-        else if (left >= 2) { gl_matvec_lazy_kernel<2><<<grid, GLMV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, parts); row0 += 2; }
-        else { gl_matvec_lazy_kernel<1><<<grid, GLMV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, parts); row0 += 1; }
-        (*launches)++;
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    (*launches)++;
-    return final_sum<S>(parts, (size_t)grid, nrows, out, ps, st);
-}
-
 size_t matvec_scratch_bytes(int ring, size_t nrows, int sms) {
     const size_t w = ring == RING_GL ? 24 : ring == RING_BB ? 72 : 64;
     return (size_t)mv_grid(sms) * nrows * w * 8 + 16;
 }
 
+// Sum of nothing = ZERO (ncols == 0): one CTA runs the tail over zero partials, so that a mailbox flag is still
+// published and the root still sums the other ranks.
 template <class S>
-static cudaError_t matvec_launch_t(const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v, u64* out,
-                                   void* scratch, cudaStream_t st, int sms, int* launches, const PeerSync& ps) {
-    *launches = 0;
-    if (nrows == 0) return cudaSuccess;
-    if (ncols == 0) {  // Sum of nothing = ZERO
-        (*launches)++;
-        return final_sum<S>(reinterpret_cast<u64*>(scratch), 0, nrows, out, ps, st);
-    }
-    size_t total = ncols * S::SLOTS;
-    int grid = mv_grid(sms);
-    size_t need = (total + MV_T - 1) / MV_T;
-    if ((size_t)grid > need) grid = (int)need;
-    u64* parts = reinterpret_cast<u64*>(scratch);
-    constexpr int RB = SR_MV_RB;
-    for (size_t row0 = 0; row0 < nrows; row0 += RB) {
-        matvec_partial_kernel<S, RB><<<grid, MV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, parts);
-        (*launches)++;
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    (*launches)++;
-    return final_sum<S>(parts, (size_t)grid, nrows, out, ps, st);
+__global__ void __launch_bounds__(MV_T)
+matvec_empty_kernel(size_t nrows, size_t row0, MvTail tail) {
+    __shared__ typename S::Val red[MV_T];
+    __shared__ int sflag[2];
+    const int rb = (nrows - row0 < (size_t)SR_MV_RB) ? (int)(nrows - row0) : SR_MV_RB;
+    if (threadIdx.x < rb * S::SLOTS)
+        S::store(tail.partial + (row0 + threadIdx.x / S::SLOTS) * S::ELEM_U64 + (threadIdx.x % S::SLOTS) * S::SLOT_U64,
+                 S::zero());
+    mv_tail<S>(tail, nrows, row0, rb, red, sflag);
 }
 
-// ps (optional): `out` is a slot of the root's mailbox; see PeerSync
+#ifndef SR_GLK_NS
+#define SR_GLK_NS 4
+#endif
+#ifndef SR_GLK_CS
+#define SR_GLK_CS 128
+#endif
+template <class S>
+static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
+                                   u64* out, void* scratch, unsigned* counter, cudaStream_t st, int sms, int* launches,
+                                   const PeerSync& ps) {
+    *launches = 0;
+    if (nrows == 0) return cudaSuccess;
+    MvTail tail = {};
+    tail.partial = reinterpret_cast<u64*>(scratch);
+    tail.out = out;
+    tail.counter = counter;
+    tail.ps = ps;
+    constexpr int RB = SR_MV_RB;
+    for (size_t row0 = 0; row0 < nrows; row0 += RB) {
+        tail.last_pass = (row0 + RB >= nrows) ? 1 : 0;
+        cudaError_t e = cudaSuccess;
+        if (ncols == 0) {
+            matvec_empty_kernel<S><<<1, MV_T, 0, st>>>(nrows, row0, tail);
+            e = cudaGetLastError();
+        } else if (ring == RING_GL) {
+            const size_t left = nrows - row0;
+            const int mg = mv_grid(sms);
+            if (left >= 4) e = gl_k6_launch<4, SR_GLK_NS, SR_GLK_CS>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
+            else if (left == 3) e = gl_k6_launch<3, SR_GLK_NS, SR_GLK_CS>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
+            else if (left == 2) e = gl_k6_launch<2, SR_GLK_NS, SR_GLK_CS>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
+            else e = gl_k6_launch<1, SR_GLK_NS, SR_GLK_CS>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
+        } else {
+            const size_t total = ncols * S::SLOTS;
+            int grid = mv_grid(sms);
+            const size_t need = (total + MV_T - 1) / MV_T;
+            if ((size_t)grid > need) grid = (int)need;
+            matvec_partial_kernel<S, RB><<<grid, MV_T, 0, st>>>(d_rows, nrows, row0, ncols, v, tail);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) return e;
+        (*launches)++;
+    }
+    return cudaSuccess;
+}
+
+// ps (optional): the result goes to / through the root's mailbox; see PeerSync
 cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v, u64* out,
-                          void* scratch, cudaStream_t st, int sms, int* launches, const PeerSync* ps) {
+                          void* scratch, unsigned* counter, cudaStream_t st, int sms, int* launches,
+                          const PeerSync* ps) {
     const PeerSync none = {};
     const PeerSync& p = ps ? *ps : none;
     switch (ring) {
-    case RING_GL: return gl_matvec_launch(d_rows, nrows, ncols, v, out, scratch, st, sms, launches, p);
-    case RING_BB: return matvec_launch_t<BBSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches, p);
-    case RING_SP: return matvec_launch_t<SPSlot>(d_rows, nrows, ncols, v, out, scratch, st, sms, launches, p);
+    case RING_GL: return matvec_launch_t<GLSlot>(ring, d_rows, nrows, ncols, v, out, scratch, counter, st, sms, launches, p);
+    case RING_BB: return matvec_launch_t<BBSlot>(ring, d_rows, nrows, ncols, v, out, scratch, counter, st, sms, launches, p);
+    case RING_SP: return matvec_launch_t<SPSlot>(ring, d_rows, nrows, ncols, v, out, scratch, counter, st, sms, launches, p);
     }
     return cudaErrorInvalidValue;
 }

@@ -13,7 +13,10 @@ struct GLSlot {
     struct Val { u64 c[3]; };
     SR_D static Val load(const u64* p) { Val v; v.c[0] = __ldcs(p); v.c[1] = __ldcs(p + 1); v.c[2] = __ldcs(p + 2); return v; }
     SR_D static Val load_cached(const u64* p) { Val v; v.c[0] = p[0]; v.c[1] = p[1]; v.c[2] = p[2]; return v; }
+    // coherent load (bypasses L1): data another CTA or another GPU has just written
+    SR_D static Val load_cv(const u64* p) { Val v; v.c[0] = __ldcv(p); v.c[1] = __ldcv(p + 1); v.c[2] = __ldcv(p + 2); return v; }
     SR_D static void store(u64* p, const Val& v) { p[0] = v.c[0]; p[1] = v.c[1]; p[2] = v.c[2]; }
+    SR_D static void store_poison(u64* p) { p[0] = p[1] = p[2] = ~0ull; }
     SR_D static Val zero() { Val v; v.c[0] = v.c[1] = v.c[2] = 0; return v; }
     // gl:: arithmetic is weak-form (gl_ring.cuh); values stored in Val are kept canonical
     SR_D static Val mul(const Val& a, const Val& b) {
@@ -69,9 +72,19 @@ struct BBSlot {
         for (int i = 0; i < 9; i++) v.c[i] = q[2 * i];
         return v;
     }
+    SR_D static Val load_cv(const u64* p) {
+        Val v;
+#pragma unroll
+        for (int i = 0; i < 9; i++) v.c[i] = (u32)__ldcv(p + i);
+        return v;
+    }
     SR_D static void store(u64* p, const Val& v) {
 #pragma unroll
         for (int i = 0; i < 9; i++) p[i] = v.c[i];
+    }
+    SR_D static void store_poison(u64* p) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) p[i] = ~0ull;
     }
     SR_D static Val zero() {
         Val v;
@@ -112,10 +125,18 @@ struct SPSlot {
         v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
         return v;
     }
+    SR_D static Val load_cv(const u64* p) {
+        Val v;
+        uint4 lo = __ldcv(reinterpret_cast<const uint4*>(p)), hi = __ldcv(reinterpret_cast<const uint4*>(p) + 1);
+        v.v[0] = lo.x; v.v[1] = lo.y; v.v[2] = lo.z; v.v[3] = lo.w;
+        v.v[4] = hi.x; v.v[5] = hi.y; v.v[6] = hi.z; v.v[7] = hi.w;
+        return v;
+    }
     SR_D static void store(u64* p, const Val& v) {
         reinterpret_cast<uint4*>(p)[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
         reinterpret_cast<uint4*>(p)[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
     }
+    SR_D static void store_poison(u64* p) { p[0] = p[1] = p[2] = p[3] = ~0ull; }
     SR_D static Val zero() {
         Val v;
 #pragma unroll

@@ -7,8 +7,9 @@ The reference has no counterpart (it is single-process); the single-GPU semantic
 Matrix::checked_mul_vec (linear_algebra/src/matrix.rs:168-178).
 
 Two exchange paths: `sharded_commit` (NCCL all-gather of the partials, then sr_modsum_partials on rank 0) and
-`PeerCommit` (the partials are stored straight into the root's HBM over NVLink by the kernel that produces them and
-summed by a kernel that acquires per-rank flags: no collective call on the data path).
+`PeerCommit` (the partials are stored straight into the root's HBM over NVLink by the tail of the kernel that
+produces them; the tail of the root's own kernel acquires the per-rank flags and sums: one launch per rank and no
+collective call on the data path).
 """
 from __future__ import annotations
 
@@ -56,26 +57,38 @@ def sharded_commit(matrix_shard, v_shard, world: int, rank: int, group=None, par
     return modsum_fn(gathered, world, nrows)
 
 
+class CommitTimeout(RuntimeError):
+    """A wait inside a commitment kernel ran out of its budget (a lost or very late peer): the result is invalid."""
+
+
 class PeerCommit:
     """Column-sharded commitment over NVLink peer memory (sr_mailbox_* / sr_commit_* of the C ABI).
 
     The root rank owns a mailbox in its HBM; every rank maps it through CUDA IPC (the 64-byte handle travels once,
-    at construction, through `exchange`, by default torch.distributed.broadcast_object_list).  Per commitment the last
-    kernel of each rank's partial product stores its nrows partial elements straight into the root's mailbox and
-    publishes an epoch flag; the root's reduction kernel acquires the flags and adds the partials mod p.  No NCCL
-    call and no host synchronisation on the data path.
+    at construction, through `exchange`, by default torch.distributed.broadcast_object_list, followed by a barrier so
+    that no rank starts before all have opened the mailbox).  Per commitment every rank launches ONE kernel per
+    four matrix rows: its tail stores the rank's partial elements straight into the root's mailbox and publishes an
+    epoch flag; on the root the same tail then acquires the flags of all ranks and adds the partials mod p
+    (`fused=True`, sr_commit_root).  No NCCL call, no host synchronisation and no separate reduction kernel on the
+    data path.  With `fused=False` the root sends like everybody else and runs sr_commit_reduce as a second kernel.
 
-    `ranks_here` > 1 emulates several ranks inside ONE process on one GPU (tests): the shards are sent one after the
-    other with rank ids 0..ranks_here-1 into the process's own mailbox.
+    Calls are asynchronous.  A rank that is later than the mailbox's wait budget (`timeout_s`, default 4 s) makes
+    the kernels give up instead of hanging the GPU: the result is then all-ones limbs and `check()` /
+    `synchronize()` raise CommitTimeout.  Call one of them before trusting a result.
+
+    `ranks_here` emulation (tests): several ranks inside ONE process on one GPU send one after the other with
+    `send(..., as_rank=r)` into the process's own mailbox, the root's share last (`root_commit`) or followed by
+    `reduce`.
     """
 
-    def __init__(self, config, nrows_max, world, rank, ctx, root=0, exchange=None, device_epochs=False):
+    def __init__(self, config, nrows_max, world, rank, ctx, root=0, exchange=None, device_epochs=False, fused=True,
+                 timeout_s=None):
         """device_epochs: the kernels count the commitments themselves (epoch argument 0), so that every step issues
         identical launches and can be captured in a CUDA graph."""
         import ctypes as C
         from . import _lib as L
         self.config, self.world, self.rank, self.root, self.ctx = config, world, rank, root, ctx
-        self.nrows_max, self.epoch, self.device_epochs = nrows_max, 0, device_epochs
+        self.nrows_max, self.epoch, self.device_epochs, self.fused = nrows_max, 0, device_epochs, fused
         self.box = C.c_void_p()
         handle = None
         if rank == root:
@@ -83,6 +96,7 @@ class PeerCommit:
             ctx.check(L.lib.sr_mailbox_create(ctx.h, config.ring_id, nrows_max, world, C.byref(self.box), buf),
                       "sr_mailbox_create")
             handle = buf.raw
+        barrier = None
         if exchange is None and world > 1:
             import torch.distributed as dist
 
@@ -90,14 +104,18 @@ class PeerCommit:
                 obj = [h]
                 dist.broadcast_object_list(obj, src=root)
                 return obj[0]
+            barrier = dist.barrier
         if world > 1 and exchange is not None:
             handle = exchange(handle)
             if rank != root:
                 ctx.check(L.lib.sr_mailbox_open(ctx.h, config.ring_id, nrows_max, world, handle, C.byref(self.box)),
                           "sr_mailbox_open")
+        if timeout_s is not None:
+            ctx.check(L.lib.sr_mailbox_set_timeout(ctx.h, self.box, int(timeout_s * 1e9)), "sr_mailbox_set_timeout")
+        if barrier is not None:
+            barrier()  # nobody commits before every rank has the mailbox mapped
 
-    def send(self, matrix_shard, v_shard, as_rank=None):
-        """This rank's share of the product, written into the root's mailbox (asynchronous)."""
+    def _product(self, matrix_shard, v_shard, as_rank, out):
         import ctypes as C
         from . import _lib as L
         from .rings import _ptr_loc
@@ -109,13 +127,28 @@ class PeerCommit:
         for i, r in enumerate(matrix_shard.vals):
             ptrs[i] = _ptr_loc(r.data)[0]
         self.ctx.use_torch_stream()
-        rc = L.lib.sr_commit_send(self.ctx.h, cfg.ring_id, ptrs, matrix_shard.nrows, matrix_shard.ncols, pv, nv,
-                                  self.box, self.rank if as_rank is None else as_rank,
-                                  0 if self.device_epochs else self.epoch)
-        self.ctx.check(rc, "sr_commit_send")
+        rank = self.rank if as_rank is None else as_rank
+        epoch = 0 if self.device_epochs else self.epoch
+        if out is None:
+            rc = L.lib.sr_commit_send(self.ctx.h, cfg.ring_id, ptrs, matrix_shard.nrows, matrix_shard.ncols, pv, nv,
+                                      self.box, rank, epoch)
+            self.ctx.check(rc, "sr_commit_send")
+        else:
+            rc = L.lib.sr_commit_root(self.ctx.h, cfg.ring_id, ptrs, matrix_shard.nrows, matrix_shard.ncols, pv, nv,
+                                      self.box, rank, epoch, C.c_void_p(out.data_ptr()))
+            self.ctx.check(rc, "sr_commit_root")
+
+    def send(self, matrix_shard, v_shard, as_rank=None):
+        """This rank's share of the product, written into the root's mailbox (asynchronous)."""
+        self._product(matrix_shard, v_shard, as_rank, None)
+
+    def root_commit(self, matrix_shard, v_shard, out, as_rank=None):
+        """Root only: the root's share AND the modular sum over all ranks in one kernel (asynchronous)."""
+        self._product(matrix_shard, v_shard, as_rank, out)
+        return out
 
     def reduce(self, nrows, out):
-        """Root only: out <- sum of the partials of the current epoch mod p (asynchronous)."""
+        """Root only, two-kernel mode: out <- sum of the partials of the current epoch mod p (asynchronous)."""
         import ctypes as C
         from . import _lib as L
         self.ctx.use_torch_stream()
@@ -128,20 +161,31 @@ class PeerCommit:
         """One commitment: every rank calls it with its column shard; returns the result on the root, None elsewhere."""
         import torch
         self.epoch += 1
-        self.send(matrix_shard, v_shard)
         if self.rank != self.root:
+            self.send(matrix_shard, v_shard)
             return None
         if out is None:
             out = torch.empty(matrix_shard.nrows * self.config.limbs, dtype=v_shard.data.dtype,
                               device=v_shard.data.device)
+        if self.fused:
+            return self.root_commit(matrix_shard, v_shard, out)
+        self.send(matrix_shard, v_shard)
         return self.reduce(matrix_shard.nrows, out)
 
     def timed_out(self) -> bool:
+        """Synchronises the context's stream and reads the mailbox's error flag."""
         import ctypes as C
         from . import _lib as L
         flag = C.c_int(0)
         self.ctx.check(L.lib.sr_mailbox_error(self.ctx.h, self.box, C.byref(flag)), "sr_mailbox_error")
         return bool(flag.value)
+
+    def check(self):
+        """Raises CommitTimeout if any wait of any commitment so far gave up (synchronises the stream)."""
+        if self.timed_out():
+            raise CommitTimeout("a commitment kernel gave up waiting for a peer: results since then are invalid")
+
+    synchronize = check
 
     def close(self):
         from . import _lib as L

@@ -91,10 +91,14 @@ def test_peer_commit_emulated_ranks_at_size(S, name, kappa, m, G):
                            S.RqNTT(cfg, dev(v[lo * w:hi * w].copy()))))
         for epoch in range(3):
             pc.epoch += 1
-            for r, (A, vs) in enumerate(shards):
-                pc.send(A, vs, as_rank=r)
             out = torch.empty(kappa * w, dtype=torch.int64, device="cuda")
-            pc.reduce(kappa, out)
+            for r in range(1, G):
+                pc.send(*shards[r], as_rank=r)
+            if epoch == 1:  # two-kernel mode: the root sends as well, then the separate reduction
+                pc.send(*shards[0], as_rank=0)
+                pc.reduce(kappa, out)
+            else:           # fused: the root's product kernel sums all ranks in its tail
+                pc.root_commit(shards[0][0], shards[0][1], out, as_rank=0)
             assert np.array_equal(host(out), want), epoch
         assert not pc.timed_out()
     finally:

@@ -25,8 +25,11 @@ def host(t):
 
 
 @pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("kappa,m,G", [(4, 1030, 4), (1, 64, 2), (7, 333, 8)])
-def test_peer_commit_emulated_ranks(name, kappa, m, G):
+def test_peer_commit_emulated_ranks(name, kappa, m, G, fused):
+    """fused=False: every rank sends, then the separate reduction kernel; fused=True: ranks 1..G-1 send, then the
+    root's product kernel sums everything in its own tail (sr_commit_root)."""
     import torch
     import stark_rings_b200 as S
     from stark_rings_b200.dist import PeerCommit, shard_columns
@@ -39,35 +42,50 @@ def test_peer_commit_emulated_ranks(name, kappa, m, G):
             v = rand_raw(name, m, 50 + epoch)
             want = C.matvec(name, rows, v, threads=8)
             pc.epoch += 1
-            for r in range(G):
+            out = torch.empty(kappa * w, dtype=torch.int64, device="cuda")
+            for r in list(range(1, G)) + [0]:  # the root's share last: in one process nothing may wait for later work
                 lo, hi = shard_columns(m, G, r)
                 A = S.Matrix([S.RqNTT(cfg, dev(x[lo * w:hi * w].copy())) for x in rows])
-                pc.send(A, S.RqNTT(cfg, dev(v[lo * w:hi * w].copy())), as_rank=r)
-            out = torch.empty(kappa * w, dtype=torch.int64, device="cuda")
-            pc.reduce(kappa, out)
+                vs = S.RqNTT(cfg, dev(v[lo * w:hi * w].copy()))
+                if fused and r == 0:
+                    pc.root_commit(A, vs, out, as_rank=0)
+                else:
+                    pc.send(A, vs, as_rank=r)
+            if not fused:
+                pc.reduce(kappa, out)
             assert np.array_equal(host(out), want), epoch
-        assert not pc.timed_out()
+        pc.check()
     finally:
         pc.close()
 
 
-def test_peer_commit_lost_peer_times_out_instead_of_hanging():
-    """A rank that never sends: the root's reduction gives up after the library's 4 s budget and flags the error."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_peer_commit_lost_peer_times_out_instead_of_hanging(fused):
+    """A rank that never sends: the root gives up after the mailbox's wait budget (0.2 s here), flags the error and
+    leaves all-ones limbs (not a canonical residue) instead of a plausible commitment.  ONE kernel waits, alone on
+    the GPU."""
     import torch
     import stark_rings_b200 as S
-    from stark_rings_b200.dist import PeerCommit
+    from stark_rings_b200.dist import CommitTimeout, PeerCommit
     name = "goldilocks"
     cfg, w = S.CONFIGS[name], WORDS[name]
     ctx = S.default_context(0)
-    pc = PeerCommit(cfg, 2, 2, 0, ctx, exchange=lambda h: h)
+    pc = PeerCommit(cfg, 2, 2, 0, ctx, exchange=lambda h: h, timeout_s=0.2)
     try:
         rows = [rand_raw(name, 8, i) for i in range(2)]
         A = S.Matrix([S.RqNTT(cfg, dev(x)) for x in rows])
+        vs = S.RqNTT(cfg, dev(rand_raw(name, 8, 9)))
+        out = torch.zeros(2 * w, dtype=torch.int64, device="cuda")
         pc.epoch += 1
-        pc.send(A, S.RqNTT(cfg, dev(rand_raw(name, 8, 9))), as_rank=0)  # rank 1 stays silent
-        out = torch.empty(2 * w, dtype=torch.int64, device="cuda")
-        pc.reduce(2, out)
+        if fused:
+            pc.root_commit(A, vs, out, as_rank=0)  # rank 1 stays silent
+        else:
+            pc.send(A, vs, as_rank=0)
+            pc.reduce(2, out)
         assert pc.timed_out()
+        with pytest.raises(CommitTimeout):
+            pc.check()
+        assert (host(out) == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
     finally:
         pc.close()
 
@@ -102,12 +120,12 @@ def test_peer_commit_device_epochs_in_a_cuda_graph():
             torch.cuda.synchronize()
             assert np.array_equal(host(out), C.matvec(name, new_rows, new_v, threads=8)), it
         ctx.use_torch_stream()
-        assert not pc.timed_out()
+        pc.check()
     finally:
         pc.close()
 
 
-def _worker(rank, world, port, name, kappa, m, q, device_epochs=False):
+def _worker(rank, world, port, name, kappa, m, q, device_epochs=False, fused=True):
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -116,7 +134,7 @@ def _worker(rank, world, port, name, kappa, m, q, device_epochs=False):
     from stark_rings_b200.dist import PeerCommit, shard_columns
     cfg, w = S.CONFIGS[name], WORDS[name]
     ctx = S.Context(rank)
-    pc = PeerCommit(cfg, kappa, world, rank, ctx, device_epochs=device_epochs)
+    pc = PeerCommit(cfg, kappa, world, rank, ctx, device_epochs=device_epochs, fused=fused)
     ok = True
     for epoch in range(1, 10):
         rows = [rand_raw(name, m, 40 + i + 100 * epoch) for i in range(kappa)]
@@ -136,8 +154,10 @@ def _worker(rank, world, port, name, kappa, m, q, device_epochs=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,device_epochs", [("goldilocks", False), ("babybear", False), ("goldilocks", True)])
-def test_peer_commit_two_processes(name, device_epochs):
+@pytest.mark.parametrize("name,device_epochs,fused", [("goldilocks", False, True), ("babybear", False, True),
+                                                      ("goldilocks", True, True), ("goldilocks", False, False),
+                                                      ("stark_prime", True, True)])
+def test_peer_commit_two_processes(name, device_epochs, fused):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs on one box")
@@ -148,7 +168,7 @@ def test_peer_commit_two_processes(name, device_epochs):
     s.close()
     mpctx = mp.get_context("spawn")
     q = mpctx.Queue()
-    procs = [mpctx.Process(target=_worker, args=(r, 2, port, name, 4, 2050, q, device_epochs)) for r in range(2)]
+    procs = [mpctx.Process(target=_worker, args=(r, 2, port, name, 4, 40000, q, device_epochs, fused)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
