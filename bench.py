@@ -2,12 +2,15 @@
 """Benchmark of the stark-rings hot path on B200 (contract: see the task statement / DESIGN.md).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload ringmul|commit] [--ring bb|gl|sp] [--log2n L]
+                  [--workload ringmul|commit] [--ring bb|gl|sp] [--log2n L] [--no-extra]
 
-Default workload = BASELINE.json configs[1]: BabyBear ring, batched CRT -> slot mul -> ICRT on 2^24
-elements per GPU (weak scaling: every rank owns its own 2^24-element shard, no data-path
-collective).  A "step" is one pass of the fused ring-mul kernel over the rank's resident batch
-(inputs 2 x 9.66 GB >> 126 MB L2, so no L2 flush is needed between steps).
+Headline = BASELINE.json configs[1]: BabyBear ring, batched CRT -> slot mul -> ICRT on 2^24 elements per GPU
+(weak scaling: every rank owns its own 2^24-element shard, no data-path collective).  A "step" is one pass of the
+fused ring-mul kernel over the rank's resident batch (inputs 2 x 9.66 GB >> 126 MB L2: no L2 flush needed).
+The same run then measures the other BASELINE configs and reports them in the line's "extra" list, each with its own
+roofline and clock record: Goldilocks 2^16 and 2^24 ring mul, Starknet-prime 2^20 ring mul against the integer
+multiply-add peak measured IN THIS RUN (sr_imad_peak), and the Goldilocks 4 x 2^20 commitment strong-scaled over the
+N ranks of the run (one kernel per rank per commitment, partials exchanged through the root's NVLink mailbox).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -24,16 +27,23 @@ sys.path.insert(0, ROOT)
 RING_NAMES = {"bb": "babybear", "gl": "goldilocks", "sp": "stark_prime"}
 ELEM_BYTES = {"bb": 576, "gl": 192, "sp": 512}
 P = {"bb": 2013265921, "gl": 18446744069414584321}
+# one Starknet-prime ring mul = 120 modular multiplications x 88 (32 x 32 + 64 -> 64) multiply-adds
+SP_IMAD_PER_RING_MUL = 10560
+L2_BYTES = 126 << 20
 
 
 def measured_traffic(tag, workload, log2n):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f).get("%s:%s:%d" % (tag, workload, log2n))
-        return None if t is None else t["dram_bytes_read"] + t["dram_bytes_write"]
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel from the committed ncu captures (profiles/r0?_traffic.json)."""
+    key = "%s:%s:%d" % (tag, workload, log2n)
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f).get(key)
+            if t is not None:
+                return t["dram_bytes_read"] + t["dram_bytes_write"]
+        except Exception:
+            pass
+    return None
 
 
 def peaks():
@@ -45,18 +55,17 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions; one process for the whole run,
+    mark_begin()/mark_end() bracket each region and return its own summary."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
-        self.t_begin = self.t_end = None
+        self.t_begin = None
 
     def start(self):
-        """Starts nvidia-smi (20 ms period) and waits until it delivers samples, so that short timed
-        regions are covered; mark_begin()/mark_end() bracket the timed region."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -77,24 +86,19 @@ class ClockSampler:
         self.t_begin = time.time()
 
     def mark_end(self):
-        self.t_end = time.time()
-
-    def stop(self):
+        """Summary of the samples taken since mark_begin()."""
+        t_end = time.time()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        inside = [r for t, r in self.rows if self.t_begin <= t <= t_end + 0.03]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: the nearest samples, taken under the same load
+            near = sorted(self.rows, key=lambda tr: abs(tr[0] - t_end))[:3]
+            inside = [r for _, r in near]
+            window = "nearest samples (timed region shorter than the 20 ms sampling period)"
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [r for t, r in self.rows if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t) + 0.03]
-        window = "timed region"
-        if not inside:  # region shorter than the sampling period: use the samples taken under the same load
-            inside = [r for _, r in self.rows]
-            window = "warm-up + timed region (timed region shorter than the 20 ms sampling period)"
         for r in inside:
             if len(r) < 9:
                 continue
@@ -109,6 +113,14 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm), "window": window}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
 
 
 def gen_raw_device(torch, tag, n, seed, device):
@@ -136,25 +148,25 @@ def make_config(args, world):
     if args.workload == "ringmul":
         cfg = {"workload": "%s ring: batched CRT->slot mul->ICRT on 2^%d elements per GPU" % (RING_NAMES[tag], args.log2n),
                "ring": RING_NAMES[tag], "log2_elements_per_gpu": args.log2n,
-               "l2": "inputs >> L2 (no flush needed)" if n * ELEM_BYTES[tag] > (256 << 20) else "inputs fit L2",
+               "l2": "inputs >> L2 (no flush needed)" if n * ELEM_BYTES[tag] > (256 << 20) else "inputs fit L2: L2 flushed between steps",
                "layout": "reference layout: u64 Montgomery limbs, %d B per element" % ELEM_BYTES[tag]}
         return "ring muls/sec (CRT->mul->ICRT)", "ring_mul/s", cfg
     cfg = {"workload": "%s commit: %d x 2^%d ring matrix x vector, columns sharded over %d GPU(s)" % (
                RING_NAMES[tag], args.kappa, args.log2n, world),
            "ring": RING_NAMES[tag], "log2_columns": args.log2n, "kappa": args.kappa,
-           "l2": "matrix >> L2" if args.kappa * n * ELEM_BYTES[tag] > (256 << 20) else "matrix fits L2",
            "layout": "reference layout: u64 Montgomery limbs, %d B per element" % ELEM_BYTES[tag]}
     return "commits/sec (kappa x m ring matrix x vector)", "commit/s", cfg
 
 
-def cpu_reference_rate(tag, sample_elems, threads, repeats=1):
+def cpu_reference_rate(tag, sample_elems, threads, repeats=1, inputs=None):
     """ring muls/s of the C restatement (oracle/sr_oracle.c, -march=native) on this host."""
-    import numpy as np
     from oracle import c_oracle as C
     from tests.util import rand_raw
     name = RING_NAMES[tag]
     lib, kind = C.lib_native()
-    a, b = rand_raw(name, sample_elems, 11, edge=False), rand_raw(name, sample_elems, 12, edge=False)
+    if inputs is None:
+        inputs = (rand_raw(name, sample_elems, 11, edge=False), rand_raw(name, sample_elems, 12, edge=False))
+    a, b = inputs
     C.ring_mul(name, a[: 1024 * C.words(name)], b[: 1024 * C.words(name)], threads=1, L=lib)  # warm
     best = None
     for _ in range(repeats):
@@ -166,14 +178,14 @@ def cpu_reference_rate(tag, sample_elems, threads, repeats=1):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU algorithm (C restatement: the Rust crate cannot be
-    built here) on the box's host cores, all threads, same metric / unit / config as our arm.
-    Each step is a bounded sample of the workload.  Rank 0 only."""
+    """--impl reference: the reference's own CPU algorithm (C restatement: the Rust crate cannot be built here) on
+    the box's host cores, all threads, same metric / unit / config as our arm.  Rank 0 only.  The ring-mul arm runs
+    the FULL configuration per step when the host has the memory for it (2 x 9.66 GB of inputs + 9.66 GB of output
+    for BabyBear 2^24); otherwise, or with --cpu-sample, a bounded sample, stated in the line."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    import numpy as np
     from oracle import c_oracle as C
     from tests.util import rand_raw
     tag = args.ring
@@ -181,19 +193,34 @@ def run_reference(args):
     metric, unit, cfg = make_config(args, world)
     times = []
     if args.workload == "ringmul":
-        sample = min(1 << args.log2n, args.cpu_sample)
+        full = 1 << args.log2n
+        sample = full
+        if args.cpu_sample:
+            sample = min(full, args.cpu_sample)
+        else:
+            try:
+                import psutil
+                need = 3.3 * full * ELEM_BYTES[tag]
+                if psutil.virtual_memory().available < need:
+                    sample = min(full, 1 << 22)
+            except Exception:
+                sample = min(full, 1 << 22)
+        name = RING_NAMES[tag]
+        inputs = (rand_raw(name, sample, 11, edge=False), rand_raw(name, sample, 12, edge=False))
         for i in range(args.warmup + args.steps):
-            rate, dt, kind = cpu_reference_rate(tag, sample, cores)
+            rate, dt, kind = cpu_reference_rate(tag, sample, cores, inputs=inputs)
             if i >= args.warmup:
                 times.append(dt)
         ms = 1e3 * sum(times) / len(times)
         value = sample / (ms / 1e3)
-        what = "%d elements per step" % sample
+        what = ("the full 2^%d elements per step" % args.log2n) if sample == full else \
+            ("%d of 2^%d elements per step (rate-based metric)" % (sample, args.log2n))
+        cfg["reference_arm_elements_per_step"] = sample
     else:
-        # commit: a bounded number of columns; the reference parallelises over the kappa rows only
+        # commit: the reference parallelises over the kappa rows only (matrix.rs:174)
         name = RING_NAMES[tag]
         lib, kind = C.lib_native()
-        m = min(1 << args.log2n, 1 << 16)
+        m = 1 << args.log2n
         rows = [rand_raw(name, m, 40 + i, edge=False) for i in range(args.kappa)]
         v = rand_raw(name, m, 50, edge=False)
         for i in range(args.warmup + args.steps):
@@ -201,15 +228,14 @@ def run_reference(args):
             C.matvec(name, rows, v, threads=min(cores, args.kappa), L=lib)
             if i >= args.warmup:
                 times.append(time.perf_counter() - t0)
-        ms_sample = 1e3 * sum(times) / len(times)
-        ms = ms_sample * ((1 << args.log2n) / m)  # scaled to the full column count
+        ms = 1e3 * sum(times) / len(times)
         value = 1e3 / ms
-        what = "%d of 2^%d columns per step (time scaled linearly), %d row threads" % (m, args.log2n, min(cores, args.kappa))
+        what = "the full 2^%d columns per step, %d row threads" % (args.log2n, min(cores, args.kappa))
     line = {
         "impl": "reference", "metric": metric, "value": value, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong" if args.workload == "commit" else "weak", "vs_baseline": None,
-        "dtype": "u32" if tag == "bb" else "u64", "data": "synthetic", "config": cfg,
+        "dtype": "u64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port",
                          "sample": "%s, %s build of oracle/sr_oracle.c (C restatement of the reference algorithm; "
                                    "the Rust crate cannot be built in this image: no cargo/rustc)" % (what, kind)},
@@ -237,6 +263,359 @@ def emit(line):
     out.flush()
 
 
+class Env:
+    """Per-process state shared by the measurements."""
+
+    def __init__(self, args):
+        import torch
+        import stark_rings_b200 as S
+        self.torch, self.S, self.args = torch, S, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        self.dev = torch.device("cuda", self.local)
+        self.ctx = S.Context(self.local)
+        self.ctx.use_torch_stream()
+        self.hbm_peak, self.peak_src = peaks()
+        self.sampler = ClockSampler(self.local)
+        self.sampler.start()
+        self.flush_buf = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def flush_l2(self):
+        if self.flush_buf is None:
+            self.flush_buf = self.torch.empty(256 << 20, dtype=self.torch.uint8, device=self.dev)
+        self.flush_buf.fill_(1)
+
+    def timed_steps(self, step, steps, warmup):
+        """W untimed steps, then K steps between a barrier + synchronize on both sides, CUDA events on the launching
+        stream, max over ranks.  Returns (ms_per_step, clocks)."""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        self.sampler.mark_begin()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        self.barrier()
+        clocks = self.sampler.mark_end()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps, clocks
+
+    def timed_steps_flushed(self, step, steps, warmup):
+        """For L2-resident inputs: an L2 flush (a 256 MiB write) before every step, each step timed on its own."""
+        torch = self.torch
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        self.sampler.mark_begin()
+        ms = []
+        for _ in range(steps):
+            self.flush_l2()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        self.barrier()
+        clocks = self.sampler.mark_end()
+        return self.max_over_ranks(sum(ms) / len(ms)), clocks
+
+
+def measure_ringmul(env, tag, log2n, steps, warmup, imad_peaks=None):
+    """Fused ring mul on 2^log2n elements resident in HBM.  Returns the record and (a, b, out, cfg)."""
+    torch, S = env.torch, env.S
+    cfg = S.CONFIGS[tag]
+    n = 1 << log2n
+    a = gen_raw_device(torch, tag, n, 0x5EED ^ (1000 * env.rank + 1), env.dev)
+    b = gen_raw_device(torch, tag, n, 0x5EED ^ (1000 * env.rank + 2), env.dev)
+    out = torch.empty_like(a)
+    step = lambda: cfg.ring_mul_batch(a, b, out=out, ctx=env.ctx)
+    in_l2 = 3 * n * ELEM_BYTES[tag] <= 2 * L2_BYTES
+    launches0 = env.ctx.kernel_launches
+    if in_l2:
+        ms, clocks = env.timed_steps_flushed(step, steps, warmup)
+    else:
+        ms, clocks = env.timed_steps(step, steps, warmup)
+    launches = env.ctx.kernel_launches - launches0 - warmup
+    # the dominant (only) kernel timed alone with events on the same stream
+    ktimes = []
+    for _ in range(min(steps, 5)):
+        if in_l2:
+            env.flush_l2()
+        env.ctx.timer_start()
+        step()
+        ktimes.append(env.ctx.timer_stop())
+    k_ms = sum(ktimes) / len(ktimes)
+    alg = 3 * ELEM_BYTES[tag] * n
+    if tag == "sp" and imad_peaks is not None:
+        ach = SP_IMAD_PER_RING_MUL * n / (k_ms / 1e3) / 1e12
+        roofline = {"bound": "imad", "achieved": ach, "peak": imad_peaks[2], "unit": "T multiply-add/s",
+                    "frac": ach / imad_peaks[2], "traffic": measured_traffic(tag, "ringmul", log2n),
+                    "peak_source": "sr_imad_peak measured in this run: IMAD.WIDE.U32.X (32 x 32 + 64 -> 64 with carry), "
+                                   "the instruction the multi-limb arithmetic is made of",
+                    "imad32_peak_in_run": imad_peaks[0], "imad_wide_peak_in_run": imad_peaks[1],
+                    "frac_of_imad32_peak": ach / imad_peaks[0],
+                    "algorithmic_multiply_adds_per_launch": SP_IMAD_PER_RING_MUL * n,
+                    "hbm_frac": alg / (k_ms / 1e3) / 1e9 / env.hbm_peak, "kernel_ms": k_ms}
+    else:
+        ach = alg / (k_ms / 1e3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": env.hbm_peak, "unit": "GB/s", "frac": ach / env.hbm_peak,
+                    "traffic": measured_traffic(tag, "ringmul", log2n), "peak_source": env.peak_src, "kernel_ms": k_ms,
+                    "algorithmic_bytes_per_launch": alg}
+    rec = {"workload": "%s ring: batched CRT->slot mul->ICRT on 2^%d elements per GPU" % (RING_NAMES[tag], log2n),
+           "metric": "ring muls/sec (CRT->mul->ICRT)", "unit": "ring_mul/s", "scaling": "weak",
+           "value": n * env.world / (ms / 1e3), "ms": ms, "steps": steps, "gpu_launches": launches,
+           "l2": "inputs fit L2: L2 flushed (256 MiB write) before every step, steps timed one by one" if in_l2
+                 else "inputs >> L2 (no flush needed)",
+           "roofline": roofline, "clocks": clocks}
+    return rec, (a, b, out, cfg)
+
+
+def measure_e2e(env, tag, log2n, a, b, out, cfg, steps):
+    """The same metric through sr_ring_mul_batch(SR_HOST) on pinned HOST buffers: H2D and D2H inside the timed region."""
+    torch = env.torch
+    e2e_n = 1 << log2n
+    last = ""
+    while e2e_n >= 1 << 10:
+        try:
+            words = e2e_n * cfg.limbs
+            ha = torch.empty(words, dtype=torch.int64).pin_memory()
+            hb = torch.empty(words, dtype=torch.int64).pin_memory()
+            ho = torch.empty(words, dtype=torch.int64).pin_memory()
+            ha.copy_(a[:words])
+            hb.copy_(b[:words])
+            torch.cuda.synchronize()
+            cfg.ring_mul_batch(ha, hb, out=ho, ctx=env.ctx)  # warm-up (allocates the staging ring)
+            k = max(1, min(steps, 3))
+            env.barrier()
+            t0 = time.perf_counter()
+            for _ in range(k):
+                cfg.ring_mul_batch(ha, hb, out=ho, ctx=env.ctx)  # synchronous: returns when `ho` is complete
+            torch.cuda.synchronize()
+            dt = env.max_over_ranks((time.perf_counter() - t0) / k)
+            if env.rank == 0:
+                assert torch.equal(ho[: 64 * cfg.limbs].to(env.dev), out[: 64 * cfg.limbs])
+            h2d, d2h = 2 * words * 8, words * 8
+            gbs = (h2d + d2h) / dt / 1e9
+            return {"value": e2e_n * env.world / dt, "unit": "ring_mul/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "elements_per_gpu": e2e_n, "ms_per_step": dt * 1e3,
+                    "bound": "pcie_h2d",
+                    "h2d_gbs": h2d / dt / 1e9, "d2h_gbs": d2h / dt / 1e9, "link_gbs_both_directions": gbs,
+                    "frac_of_pcie": (h2d / dt / 1e9) / 64.0,
+                    "pcie_reference": "PCIe Gen5 x16: 64 GB/s per direction nominal; H2D carries 2/3 of the bytes and "
+                                      "bounds the step; both directions run concurrently",
+                    "note": "sr_ring_mul_batch(SR_HOST) on pinned host buffers: chunked H2D -> kernel -> D2H pipeline; "
+                            "at N > 1 all ranks share the host's memory and PCIe root complexes"}
+        except RuntimeError as ex:  # pinned allocation failed: halve
+            e2e_n //= 2
+            last = str(ex)[:120]
+    return {"value": None, "unit": "ring_mul/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+            "note": "pinned host allocation failed: " + last}
+
+
+def measure_commit(env, tag, kappa, log2m, steps, warmup, path="peer", graph=True):
+    """kappa x 2^log2m commitment, columns sharded over the ranks of the run (strong scaling).  Rotates over enough
+    distinct resident shards that the working set exceeds the L2 (one context per shard: each keeps its row table
+    resident, so a step is kernel launches only)."""
+    torch, S = env.torch, env.S
+    import ctypes
+    from stark_rings_b200 import _lib as L
+    cfg = S.CONFIGS[tag]
+    world, rank = env.world, env.rank
+    m = 1 << log2m
+    lo, hi = m * rank // world, m * (rank + 1) // world
+    m_local = hi - lo
+    shard_bytes = (kappa * m_local + m_local + kappa) * ELEM_BYTES[tag]
+    nsets = max(1, min(8, -(-4 * L2_BYTES // shard_bytes)))  # working set >= 4 x L2
+    ctxs = [env.ctx] + [S.Context(env.local) for _ in range(nsets - 1)]
+    sets = []
+    for k in range(nsets):
+        ctxs[k].use_torch_stream()
+        rows = [S.RqNTT(cfg, gen_raw_device(torch, tag, m_local, 0x5EED ^ (1000 * rank + 100 * k + 10 + i), env.dev), ctxs[k])
+                for i in range(kappa)]
+        v = S.RqNTT(cfg, gen_raw_device(torch, tag, m_local, 0x5EED ^ (1000 * rank + 100 * k + 3), env.dev), ctxs[k])
+        sets.append((S.Matrix(rows, ctxs[k]), v))
+    limbs = cfg.limbs
+    result = torch.empty(kappa * limbs, dtype=torch.int64, device=env.dev)
+    gathered = torch.empty(world * kappa * limbs, dtype=torch.int64, device=env.dev)
+    peer = None
+    if env.dist is not None and path == "peer":
+        from stark_rings_b200.dist import PeerCommit
+        peer = PeerCommit(cfg, kappa, world, rank, env.ctx, device_epochs=True)
+    counter = [0]
+
+    def step():
+        k = counter[0] % nsets
+        counter[0] += 1
+        A, v = sets[k]
+        if peer is not None:
+            return peer.commit(A, v, out=result, ctx=ctxs[k])
+        if env.dist is None:
+            ctxs[k].use_torch_stream()
+            return A.try_mul_vec(v)
+        part = A.partial_mul_vec(v)
+        env.dist.all_gather_into_tensor(gathered, part.data)  # raw limbs; an NCCL sum cannot reduce mod p
+        if rank == 0:
+            env.ctx.check(L.lib.sr_modsum_partials(env.ctx.h, cfg.ring_id, ctypes.c_void_p(gathered.data_ptr()), world,
+                                                   kappa, ctypes.c_void_p(result.data_ptr()), L.SR_DEVICE), "modsum")
+        return part
+
+    # ---- correctness of the measured path, before any number is reported: one commitment against the oracle ----
+    check = "not run"
+    try:
+        from oracle import c_oracle as C
+        import numpy as np
+        A, v = sets[0]
+        counter[0] = 0
+        y = step()
+        torch.cuda.synchronize()
+        # every rank's shard on the host -> the oracle's partial product -> modular sum via the oracle's own add
+        rows_h = [r.data.cpu().numpy().view(np.uint64) for r in A.vals]
+        v_h = v.data.cpu().numpy().view(np.uint64)
+        sample = min(m_local, 4096)
+        w = cfg.limbs
+        want_part = C.matvec(RING_NAMES[tag], [r[: sample * w].copy() for r in rows_h], v_h[: sample * w].copy(), threads=kappa)
+        A_s = S.Matrix([S.RqNTT(cfg, r.data[: sample * w].clone(), env.ctx) for r in A.vals], env.ctx)
+        env.ctx.use_torch_stream()
+        got_part = A_s.try_mul_vec(S.RqNTT(cfg, v.data[: sample * w].clone(), env.ctx)).data.cpu().numpy().view(np.uint64)
+        ok_local = bool(np.array_equal(got_part, want_part))
+        # whole-product consistency: the commit's result == the modular sum of the ranks' own full partial products
+        full_part = A.partial_mul_vec(v).data if world > 1 else None
+        ok_sum = True
+        if world == 1:  # the whole product == the modular sum of the products of its two column halves
+            half = (m_local // 2) * w
+            halves = []
+            for sl in (slice(0, half), slice(half, m_local * w)):
+                Ah = S.Matrix([S.RqNTT(cfg, r.data[sl].clone(), env.ctx) for r in A.vals], env.ctx)
+                halves.append(Ah.partial_mul_vec(S.RqNTT(cfg, v.data[sl].clone(), env.ctx)).data)
+            parts = torch.cat(halves)
+            ref = torch.empty(kappa * w, dtype=torch.int64, device=env.dev)
+            env.ctx.check(L.lib.sr_modsum_partials(env.ctx.h, cfg.ring_id, ctypes.c_void_p(parts.data_ptr()), 2,
+                                                   kappa, ctypes.c_void_p(ref.data_ptr()), L.SR_DEVICE), "modsum")
+            ok_sum = bool(torch.equal(ref, y.data))
+        if world > 1:
+            parts = torch.empty(world * kappa * w, dtype=torch.int64, device=env.dev)
+            env.dist.all_gather_into_tensor(parts, full_part)
+            if rank == 0:
+                ref = torch.empty(kappa * w, dtype=torch.int64, device=env.dev)
+                env.ctx.use_torch_stream()
+                env.ctx.check(L.lib.sr_modsum_partials(env.ctx.h, cfg.ring_id, ctypes.c_void_p(parts.data_ptr()), world,
+                                                       kappa, ctypes.c_void_p(ref.data_ptr()), L.SR_DEVICE), "modsum")
+                ok_sum = bool(torch.equal(ref, result))
+        ok = env.max_over_ranks(0.0 if (ok_local and ok_sum) else 1.0) == 0.0
+        if not ok:
+            raise SystemExit("bench.py: the commitment does not match the oracle (local %s, sum %s)" % (ok_local, ok_sum))
+        check = "one commitment verified: %d-column sample of every rank's shard against the C oracle, and the " \
+                "delivered result against the modular sum of the ranks' partial products" % sample
+    except ImportError:
+        check = "oracle not importable"
+    counter[0] = 0
+
+    # ---- timing: the nsets commitments captured in one CUDA graph when the path allows it ----
+    cuda_graph = False
+    unit_steps = nsets
+    one = lambda: [step() for _ in range(nsets)]
+    for _ in range(2):
+        one()
+    env.barrier()
+    if graph and (world == 1 or peer is not None):
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                one()
+            one = g.replay
+            cuda_graph = True
+        except Exception as ex:
+            cuda_graph = "capture failed: %s" % str(ex)[:80]
+            torch.cuda.synchronize()
+        for c in ctxs:
+            c.use_torch_stream()
+    reps = max(1, -(-steps // unit_steps))
+    launches0 = sum(c.kernel_launches for c in ctxs)
+    ms_rep, clocks = env.timed_steps(one, reps, max(1, -(-warmup // unit_steps)))
+    launches = sum(c.kernel_launches for c in ctxs) - launches0
+    ms = ms_rep / unit_steps
+    if peer is not None:
+        peer.check()  # raises if any in-kernel wait timed out: no number from a broken exchange
+    # the product kernel alone (no mailbox): what the step costs without the exchange.  Captured in a graph as well,
+    # so that the host's launch path is not what is measured.
+    outs = [torch.empty(kappa * limbs, dtype=torch.int64, device=env.dev) for _ in range(nsets)]
+
+    def products():
+        for k in range(nsets):
+            A, v = sets[k]
+            pv, nv = ctypes.c_void_p(v.data.data_ptr()), v.data.numel()
+            ptrs = (ctypes.c_void_p * kappa)(*[r.data.data_ptr() for r in A.vals])
+            ctxs[k].use_torch_stream()
+            ctxs[k].check(L.lib.sr_matvec_partial(ctxs[k].h, cfg.ring_id, ptrs, kappa, m_local, pv, nv,
+                                                  ctypes.c_void_p(outs[k].data_ptr()), L.SR_DEVICE), "sr_matvec_partial")
+    products()
+    torch.cuda.synchronize()
+    run_products = products
+    if graph:
+        try:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                products()
+            run_products = g2.replay
+        except Exception:
+            torch.cuda.synchronize()
+        for c in ctxs:
+            c.use_torch_stream()
+    k_rep, _ = env.timed_steps(run_products, max(3, reps), 2)
+    kernel_ms = k_rep / nsets
+    ach = shard_bytes / (ms / 1e3) / 1e9
+    rec = {"workload": "%s commit: %d x 2^%d ring matrix x vector, columns sharded over %d GPU(s)" % (
+               RING_NAMES[tag], kappa, log2m, world),
+           "metric": "commits/sec (kappa x m ring matrix x vector)", "unit": "commit/s", "scaling": "strong",
+           "value": 1e3 / ms, "ms": ms, "steps": reps * unit_steps,
+           "gpu_launches": launches if launches else (reps * unit_steps * ((kappa + 3) // 4)),
+           "kernels_per_commit_per_rank": (kappa + 3) // 4,
+           "exchange": "none (1 GPU)" if env.dist is None else (
+               "NVLink peer-memory mailbox: the tail of each rank's product kernel stores its partial rows into the "
+               "root's HBM and publishes a flag; the tail of the root's kernel acquires the flags and adds mod p"
+               if peer else "NCCL all_gather of raw limbs + rank-0 modular sum"),
+           "cuda_graph": cuda_graph,
+           "l2": "rotating over %d distinct resident shards per rank (%.0f MB each): working set >= 4 x L2" % (
+               nsets, shard_bytes / 1e6),
+           "product_kernel_us": kernel_ms * 1e3, "step_us": ms * 1e3,
+           "exchange_us": max(0.0, (ms - kernel_ms) * 1e3),
+           "verified": check,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": env.hbm_peak, "unit": "GB/s per GPU",
+                        "frac": ach / env.hbm_peak, "traffic": measured_traffic(tag, "commit", log2m),
+                        "peak_source": env.peak_src, "algorithmic_bytes_per_launch_per_gpu": shard_bytes,
+                        "product_kernel_frac": shard_bytes / (kernel_ms / 1e3) / 1e9 / env.hbm_peak},
+           "clocks": clocks}
+    if peer is not None:
+        peer.close()
+    return rec
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -248,14 +627,16 @@ def main():
     ap.add_argument("--ring", default=None, choices=["bb", "gl", "sp"])
     ap.add_argument("--log2n", type=int, default=None, help="log2 elements per GPU (ringmul) / columns (commit)")
     ap.add_argument("--kappa", type=int, default=4)
-    ap.add_argument("--cpu-sample", type=int, default=1 << 20, help="elements in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="elements in the CPU arm's sample (0: the full size if it fits)")
     ap.add_argument("--e2e-log2n", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (the line's `extra` list)")
     ap.add_argument("--commit-path", default="peer", choices=["peer", "nccl"],
                     help="commit workload, N > 1: how the per-rank partials reach rank 0")
-    ap.add_argument("--graph", action="store_true", help="commit workload, 1 GPU: capture the step in a CUDA graph")
+    ap.add_argument("--no-graph", action="store_true", help="commit workload: do not capture the steps in a CUDA graph")
     args = ap.parse_args()
+    default_run = args.ring is None and args.log2n is None and args.workload == "ringmul"
     if args.ring is None:
         args.ring = "gl" if args.workload == "commit" else "bb"
     if args.log2n is None:
@@ -266,210 +647,70 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
-    import torch
-
-    import stark_rings_b200 as S
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    ctx = S.Context(local)
-    ctx.use_torch_stream()
+    env = Env(args)
+    torch = env.torch
     tag = args.ring
-    cfg = S.CONFIGS[tag]
-    hbm_peak, peak_src = peaks()
+    metric, unit, config = make_config(args, env.world)
+    imad = None
+    if tag == "sp" or (default_run and not args.no_extra):
+        imad = env.ctx.imad_peak()
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    n = 1 << args.log2n
-    line = {}
-    metric, unit, config = make_config(args, world)
     if args.workload == "ringmul":
-        a = gen_raw_device(torch, tag, n, 0x5EED ^ (1000 * rank + 1), dev)
-        b = gen_raw_device(torch, tag, n, 0x5EED ^ (1000 * rank + 2), dev)
-        out = torch.empty_like(a)
-        step = lambda: cfg.ring_mul_batch(a, b, out=out, ctx=ctx)
-        units_per_step = n
-        alg_bytes_per_unit = 3 * ELEM_BYTES[tag]
-    else:
-        # Goldilocks Ajtai-style commit: kappa x m matrix times vector, columns sharded over ranks
-        m_local = n // world
-        rows = [S.RqNTT(cfg, gen_raw_device(torch, tag, m_local, 0x5EED ^ (1000 * rank + 10 + i), dev), ctx)
-                for i in range(args.kappa)]
-        v = S.RqNTT(cfg, gen_raw_device(torch, tag, m_local, 0x5EED ^ (1000 * rank + 3), dev), ctx)
-        A = S.Matrix(rows, ctx)
-        limbs = cfg.limbs
-        gathered = torch.empty(world * args.kappa * limbs, dtype=torch.int64, device=dev)
-        result = torch.empty(args.kappa * limbs, dtype=torch.int64, device=dev)
-        import ctypes
-        from stark_rings_b200 import _lib as L
-
-        peer = None
-        if dist is not None and args.commit_path == "peer":
-            # partials go straight into rank 0's HBM over NVLink from the kernel that produces them; rank 0's
-            # reduction kernel acquires the per-rank flags (stark_rings_b200/dist.py PeerCommit)
-            from stark_rings_b200.dist import PeerCommit
-            peer = PeerCommit(cfg, args.kappa, world, rank, ctx, device_epochs=args.graph)
-        config["exchange"] = "none (1 GPU)" if dist is None else (
-            "NVLink peer-memory mailbox fused into the producing / reducing kernels" if peer else
-            "NCCL all_gather of raw limbs + rank-0 modular sum")
-
-        def step():
-            if peer is not None:
-                return peer.commit(A, v, out=result)
-            part = A.partial_mul_vec(v)
-            if dist is not None:
-                dist.all_gather_into_tensor(gathered, part.data)  # raw limbs; an NCCL sum cannot reduce mod p
-                if rank == 0:
-                    ctx.check(L.lib.sr_modsum_partials(ctx.h, cfg.ring_id, ctypes.c_void_p(gathered.data_ptr()),
-                                                       world, args.kappa, ctypes.c_void_p(result.data_ptr()),
-                                                       L.SR_DEVICE), "modsum")
-            return part
-        units_per_step = 1
-        alg_bytes_per_unit = (args.kappa * m_local + m_local + args.kappa) * ELEM_BYTES[tag]
-
-    # ---- device-resident timing ---------------------------------------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    launches_per_step = None
-    if args.workload == "commit" and args.graph and (world == 1 or peer is not None):
-        # optional: capture the step's kernels in a CUDA graph (the row table is already resident, see sr_capi.cu).
-        # 1 GPU: gain 1% at kappa = 4, m = 2^20.  N GPUs: only the peer-memory path can be captured (device-resident
-        # epochs, no collective call in the step); with NCCL in the step the capture hung in round 1.
-        try:
-            l0 = ctx.kernel_launches
-            step()
-            launches_per_step = ctx.kernel_launches - l0
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step()
-            step = graph.replay
-            for _ in range(3):
-                step()
-            config["cuda_graph"] = True
-        except Exception as ex:  # keep the eager path
-            config["cuda_graph"] = "capture failed: %s" % str(ex)[:80]
-            torch.cuda.synchronize()
-        barrier()
-    launches0 = ctx.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    sampler.mark_begin()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    sampler.mark_end()
-    clocks = sampler.stop()
-    total_ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = ctx.kernel_launches - launches0
-    if launches == 0 and launches_per_step:  # graph replays do not pass through the launch counter
-        launches = launches_per_step * args.steps
-    ms_per_step = total_ms / args.steps
-    strong = args.workload == "commit"
-    value = (units_per_step * (1 if strong else world)) / (ms_per_step / 1e3)
-
-    # roofline of the dominant kernel: its own launches, timed alone with events on the same stream
-    ctx.use_torch_stream()  # (a graph capture leaves the context on the capture stream)
-    ktimes = []
-    for _ in range(min(args.steps, 5)):
-        ctx.timer_start()
-        step()
-        ktimes.append(ctx.timer_stop())
-    k_ms = sum(ktimes) / len(ktimes)
-    if args.workload == "ringmul":
-        achieved = alg_bytes_per_unit * units_per_step / (k_ms / 1e3) / 1e9
-    else:
-        achieved = alg_bytes_per_unit / (k_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": measured_traffic(tag, args.workload, args.log2n), "peak_source": peak_src, "kernel_ms": k_ms,
-                "algorithmic_bytes_per_launch": alg_bytes_per_unit * (units_per_step if args.workload == "ringmul" else 1)}
-
-    # ---- end to end through the C ABI with HOST buffers -----------------------------------------
-    e2e = None
-    if not args.no_e2e and args.workload == "ringmul":
-        e2e_n = 1 << (args.e2e_log2n if args.e2e_log2n is not None else args.log2n)
+        head, (a, b, out, cfg) = measure_ringmul(env, tag, args.log2n, args.steps, args.warmup, imad)
         e2e = None
-        while e2e is None and e2e_n >= 1 << 10:
-            try:
-                words = e2e_n * cfg.limbs
-                ha = torch.empty(words, dtype=torch.int64).pin_memory()
-                hb = torch.empty(words, dtype=torch.int64).pin_memory()
-                ho = torch.empty(words, dtype=torch.int64).pin_memory()
-                ha.copy_(a[:words])
-                hb.copy_(b[:words])
-                torch.cuda.synchronize()
-                cfg.ring_mul_batch(ha, hb, out=ho, ctx=ctx)  # warm-up (allocates the staging ring)
-                k = max(1, min(args.steps, 3))
-                barrier()
-                t0 = time.perf_counter()
-                for _ in range(k):
-                    cfg.ring_mul_batch(ha, hb, out=ho, ctx=ctx)  # synchronous: returns when `ho` is complete
-                torch.cuda.synchronize()
-                dt = max_over_ranks((time.perf_counter() - t0) / k)
-                if rank == 0:
-                    assert torch.equal(ho[: 64 * cfg.limbs].to(dev), out[: 64 * cfg.limbs])
-                e2e = {"value": e2e_n * world / dt, "unit": unit, "h2d_bytes_per_step": 2 * words * 8,
-                       "d2h_bytes_per_step": words * 8, "elements_per_gpu": e2e_n, "ms_per_step": dt * 1e3,
-                       "note": "sr_ring_mul_batch(SR_HOST) on pinned host buffers: chunked H2D -> kernel -> D2H pipeline"}
-                del ha, hb, ho
-            except RuntimeError as ex:  # pinned allocation failed: halve
-                e2e = None
-                e2e_n //= 2
-                last = str(ex)[:120]
-        if e2e is None:
-            e2e = {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                   "note": "pinned host allocation failed: " + last}
+        if not args.no_e2e:
+            e2e = measure_e2e(env, tag, args.e2e_log2n if args.e2e_log2n is not None else args.log2n, a, b, out, cfg,
+                              args.steps)
+        del a, b, out
+        torch.cuda.empty_cache()
+        strong = False
+    else:
+        head = measure_commit(env, tag, args.kappa, args.log2n, args.steps, args.warmup, args.commit_path,
+                              not args.no_graph)
+        for k in ("exchange", "cuda_graph", "l2", "product_kernel_us", "step_us", "exchange_us", "verified",
+                  "kernels_per_commit_per_rank"):
+            config[k] = head[k]
+        e2e = None
+        strong = True
 
     cpu = None
-    if rank == 0 and not args.no_cpu and world == 1 and args.workload == "ringmul":
+    if env.rank == 0 and not args.no_cpu and env.world == 1 and args.workload == "ringmul":
         cores = os.cpu_count() or 1
-        sample = min(n, args.cpu_sample)
+        sample = min(1 << args.log2n, args.cpu_sample or (1 << 20))
         rate, dt, kind = cpu_reference_rate(tag, sample, cores)
         rate1, dt1, _ = cpu_reference_rate(tag, max(1024, sample // 16), 1)
         cpu = {"value": rate, "unit": unit, "cores": cores, "kind": "port",
                "sample": "%d elements (%.1f s wall on %d threads), %s build of oracle/sr_oracle.c" % (sample, dt, cores, kind),
                "value_1thread": rate1}
 
-    if rank == 0:
+    extra = []
+    if default_run and not args.no_extra:
+        # the other BASELINE configs, measured in this process
+        for etag, elog in (("gl", 16), ("gl", 24), ("sp", 20)):
+            rec, bufs = measure_ringmul(env, etag, elog, max(args.steps, 10), args.warmup, imad)
+            del bufs
+            torch.cuda.empty_cache()
+            extra.append(rec)
+        extra.append(measure_commit(env, "gl", 4, 20, max(args.steps, 40), args.warmup, args.commit_path,
+                                    not args.no_graph))
+    env.sampler.stop()
+
+    if env.rank == 0:
         line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": metric, "value": head["value"], "unit": unit, "n_gpus": env.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms"], "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "u32" if tag == "bb" else "u64", "data": "synthetic",
+            "dtype": "u64", "data": "synthetic",
             "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": head["clocks"], "e2e": e2e, "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+            "cpu_baseline": cpu,
         }
+        if extra:
+            line["extra"] = extra
         emit(line)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if env.dist is not None:
+        env.dist.barrier()
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

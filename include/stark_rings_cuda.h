@@ -71,6 +71,12 @@ int sr_d2h(sr_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* 
 int sr_timer_start(sr_ctx* ctx);
 int sr_timer_stop(sr_ctx* ctx, float* ms);    /* synchronises; elapsed since sr_timer_start */
 
+/* Measured integer multiply-add peaks of the context's device, in 10^12 operations per second: tops3[0] 32-bit IMAD,
+ * tops3[1] IMAD.WIDE.U32 (32 x 32 + 64 -> 64), tops3[2] the carry-chained IMAD.WIDE.U32.X the multi-limb kernels use.
+ * The roofline denominator of the Starknet-prime kernels (bench.py measures it in the run it reports).  Synchronous,
+ * about 10 ms. */
+int sr_imad_peak(sr_ctx* ctx, double* tops3);
+
 /* ---- batched conversions and products ------------------------------------------------------
  * Replaces  CRT::elementwise_crt / ICRT::elementwise_icrt            (crt.rs:10-25, 34-49)
  *           CyclotomicConfig::{crt_in_place, icrt_in_place}           (ring_config.rs:27,34)

@@ -49,6 +49,7 @@ _sig("sr_h2d", _int, _vp, _vp, _vp, _sz)
 _sig("sr_d2h", _int, _vp, _vp, _vp, _sz)
 _sig("sr_timer_start", _int, _vp)
 _sig("sr_timer_stop", _int, _vp, ctypes.POINTER(ctypes.c_float))
+_sig("sr_imad_peak", _int, _vp, ctypes.POINTER(ctypes.c_double))
 _sig("sr_crt_batch", _int, _vp, _int, _vp, _sz, _int)
 _sig("sr_icrt_batch", _int, _vp, _int, _vp, _sz, _int)
 _sig("sr_ntt_mul_batch", _int, _vp, _int, _vp, _vp, _sz, _int)
@@ -86,7 +87,7 @@ for _tag in ("gl", "bb", "sp"):
 EXPORTS = [
     "sr_init", "sr_destroy", "sr_last_error", "sr_version", "sr_set_stream", "sr_reset_stream", "sr_sync", "sr_elem_limbs",
     "sr_kernel_launches", "sr_dev_alloc", "sr_dev_free", "sr_host_alloc", "sr_host_free", "sr_h2d", "sr_d2h",
-    "sr_timer_start", "sr_timer_stop", "sr_crt_batch", "sr_icrt_batch", "sr_ntt_mul_batch", "sr_ring_mul_batch",
+    "sr_timer_start", "sr_timer_stop", "sr_imad_peak", "sr_crt_batch", "sr_icrt_batch", "sr_ntt_mul_batch", "sr_ring_mul_batch",
     "sr_matvec", "sr_matvec_partial", "sr_modsum_partials", "sr_reduce_batch", "sr_rot_batch",
     "sr_gadget_decompose", "sr_gadget_recompose", "sr_sparse_matvec", "sr_matmat", "sr_ntt_scale_batch",
     "sr_mailbox_create", "sr_mailbox_open", "sr_mailbox_destroy", "sr_mailbox_error", "sr_mailbox_set_timeout", "sr_commit_send", "sr_commit_root",

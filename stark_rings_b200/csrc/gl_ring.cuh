@@ -93,6 +93,25 @@ SR_D u64 add(u64 a, u64 b) {
         : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
     return plus_eps_if(lo, hi, m);              // + EPS when the sum wrapped: a + b - 2^64 < p, no second wrap
 }
+// The same sum with the correction as two PREDICATED adds of 2^32 - 1 (lo + 0xFFFFFFFF, carry into hi): four
+// instructions on the ALU pipe and no multiply-add (the mat-vec kernels, whose wide multiply-add pipe is the
+// binding unit).  a weak, b canonical -> weak.
+SR_D u64 add_cc(u64 a, u64 b) {
+    u32 lo, hi;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        ".reg .pred p;\n\t"
+        "add.cc.u32   %0, %2, %4;\n\t"
+        "addc.cc.u32  %1, %3, %5;\n\t"
+        "addc.u32     m, 0, 0;\n\t"
+        "setp.ne.u32  p, m, 0;\n\t"
+        "@p add.cc.u32  %0, %0, 0xffffffff;\n\t"
+        "@p addc.u32    %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(lo), "=&r"(hi)
+        : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
+    return mk64(lo, hi);
+}
 SR_D u64 sub(u64 a, u64 b) {
     u32 lo, hi;
     asm("{\n\t"
@@ -131,6 +150,7 @@ SR_HD u64 add(u64 a, u64 b) {
     bool over = (s < a) | (s >= P);
     return over ? s + EPS : s;
 }
+SR_HD u64 add_cc(u64 a, u64 b) { return add(a, b); }
 SR_HD u64 sub(u64 a, u64 b) {
     a = canon(a);
     u64 d = a - b;

@@ -38,6 +38,8 @@ cudaError_t matmat_launch(int ring, const u64* const* a_rows, const u64* const* 
 cudaError_t scale_launch(int ring, u64* a, const u64* r, size_t n, cudaStream_t st);
 // canonical (de)serialization (sr_serial.cu): op 0 limbs -> bytes, op 1 bytes -> limbs
 cudaError_t serial_launch(int ring, int op, const void* in, void* out, size_t nfe, int* bad, cudaStream_t st);
+// integer multiply-add peaks of the device (sr_peak.cu)
+cudaError_t imad_peak_measure(int sms, cudaStream_t st, double* tops);
 }  // namespace sr
 
 using sr::u64;
@@ -688,6 +690,15 @@ int sr_timer_stop(sr_ctx* ctx, float* ms) {
     CU(cudaEventRecord(ctx->t1, ctx->stream));
     CU(cudaEventSynchronize(ctx->t1));
     CU(cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return SR_OK;
+}
+
+int sr_imad_peak(sr_ctx* ctx, double* tops3) {
+    if (!ctx || !tops3) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(sr::imad_peak_measure(ctx->sms, ctx->stream, tops3));
+    ctx->launches += 18;
     return SR_OK;
 }
 

@@ -12,6 +12,8 @@
 // rows), with no separate reduction kernel, no collective call and no host synchronisation.
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #define SR_GL_EPS_ON_ALU  // these kernels are bound by the multiply-add pipe: see gl_ring.cuh plus_eps_if
 
 #include "bb_ring.cuh"
@@ -171,76 +173,114 @@ SR_D void mv_tail(const MvTail& t, size_t nrows, size_t row0, int rb, typename S
 // (Thread counts are kept at multiples of 128: ptxas sizes the register budget for the thread count rounded up to
 // 128, so a dedicated producer warp on top of 4 x 128 consumers cost 24 registers per thread and spilled.  The
 // copies are issued by thread 0 of the CTA instead, one stage behind the one being consumed.)
-template <int RB, int NS, int CS>
+// A thread owns SPT slots of a chunk, CS apart: CS is a multiple of 8, so they have the same slot index and feed the
+// same six accumulators; the per-chunk costs (barrier wait, stage release, loop control) are paid once per SPT slots.
+// The first version of this kernel (one slot per trip, 64-bit chunk arithmetic) issued 250 instructions per slot and
+// row of which 82 were arithmetic, and ran at the issue limit.
+template <int RB, int NS, int CS, int SPT>
 __global__ void __launch_bounds__(CS * RB, (CS * RB <= 128 ? 4 : (CS * RB <= 256 ? 2 : 1)))
 gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
                     const u64* __restrict__ v, MvTail tail) {
     typedef GLSlot S;
-    constexpr uint32_t ROWB = CS * 24;           // bytes per row per stage
-    constexpr int STAGE_U64 = (RB + 1) * CS * 3;
+    constexpr int CHUNK = CS * SPT;                 // slots per chunk
+    constexpr uint32_t ROWB = CHUNK * 24;           // bytes per row per stage
+    constexpr int ROW_U64 = CHUNK * 3, STAGE_U64 = (RB + 1) * ROW_U64;
     extern __shared__ __align__(128) unsigned char smem[];
-    u64* stage = reinterpret_cast<u64*>(smem);   // [NS][RB + 1][CS * 3]
+    u64* stage = reinterpret_cast<u64*>(smem);      // [NS][RB + 1][CHUNK * 3]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)NS * (RB + 1) * ROWB);
     uint64_t* empty = full + NS;
     int* sflag = reinterpret_cast<int*>(empty + NS);
+    const u64** srow = reinterpret_cast<const u64**>(sflag + 4);  // the RB row pointers (read by the issuing thread)
     S::Val* red = reinterpret_cast<S::Val*>(smem);  // the stages are dead once the column loop is over
 
     const int slot = threadIdx.x % CS, grp = threadIdx.x / CS;  // row row0 + grp
     const size_t total = ncols * S::SLOTS;
-    const size_t nchunks = (total + CS - 1) / CS;
-    const size_t my_chunks = (nchunks > blockIdx.x) ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned nchunks = (unsigned)((total + CHUNK - 1) / CHUNK);
+    const int last_valid = (int)(total - (size_t)(nchunks - 1) * CHUNK);  // slots in the globally last chunk
+    const int my_chunks = (nchunks > blockIdx.x) ? (int)((nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
-    auto issue = [&](size_t it) {  // thread 0 only: chunk `it` of this CTA into stage it % NS
-        const int s = (int)(it % NS);
-        const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
-        const uint32_t bytes = (uint32_t)(((total - slot0 < (size_t)CS) ? (total - slot0) : (size_t)CS) * 24);
+    auto issue = [&](int it, int s) {  // thread 0 only: chunk `it` of this CTA into stage s
+        const unsigned chunk = blockIdx.x + (unsigned)it * gridDim.x;
+        const size_t slot0 = (size_t)chunk * CHUNK;
+        const uint32_t bytes = (uint32_t)((chunk == nchunks - 1 ? last_valid : CHUNK) * 24);
         mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
         u64* dst = stage + (size_t)s * STAGE_U64;
         tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
 #pragma unroll
-        for (int r = 0; r < RB; r++) {
-            const u64* rp = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
-            tma_load_1d(dst + (size_t)(r + 1) * CS * 3, rp + slot0 * 3, bytes, &full[s]);
-        }
+        for (int r = 0; r < RB; r++) tma_load_1d(dst + (size_t)(r + 1) * ROW_U64, srow[r] + slot0 * 3, bytes, &full[s]);
     };
     if (threadIdx.x == 0) {
+        // (the row pointers are parked in shared memory: re-reading the table from global memory at every refill put
+        // four dependent L2 round trips into the one warp every stage waits for)
+        for (int r = 0; r < RB; r++) srow[r] = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
         for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], RB * CS / 32); }
         mbar_fence_init();
-        for (size_t it = 0; it < (size_t)NS && it < my_chunks; it++) issue(it);
+        for (int it = 0; it < NS && it < my_chunks; it++) issue(it, it);
     }
     __syncthreads();
 
     gl::Acc P0, P1, P2, P01, P02, P12;
     gl::acc_zero(P0); gl::acc_zero(P1); gl::acc_zero(P2); gl::acc_zero(P01); gl::acc_zero(P02); gl::acc_zero(P12);
 
-    for (size_t it = 0; it < my_chunks; it++) {
-        const int s = (int)(it % NS);
+    const u64* tbase = stage + slot * 3;  // this thread's first slot of the vector in stage 0
+    // one chunk: stage s holds chunk `it` of this CTA.  RAGGED: the globally last chunk may be short (stale bytes of
+    // an earlier chunk sit behind it in the stage): only then are the loads guarded.
+    auto step = [&](int it, int s, uint32_t phase, auto ragged) {
         if (threadIdx.x == 0 && it > 0 && it - 1 + NS < my_chunks) {
-            // refill the stage that was consumed one trip ago (every warp has arrived on its `empty` barrier by now,
-            // or is about to: no CTA barrier, and the other warps never wait for this one)
-            mbar_wait(&empty[(it - 1) % NS], (uint32_t)(((it - 1) / NS) & 1));
-            issue(it - 1 + NS);
+            // refill the stage that was consumed one trip ago (no CTA barrier: the other warps never wait for this
+            // one, and this one only waits for warps that lag a whole trip behind)
+            const int ps = (s + NS - 1) % NS;
+            mbar_wait(&empty[ps], s == 0 ? (phase ^ 1) : phase);
+            issue(it - 1 + NS, ps);
         }
         __syncwarp();
-        mbar_wait(&full[s], (uint32_t)((it / NS) & 1));
-        const size_t slot0 = (blockIdx.x + it * gridDim.x) * CS;
-        const bool live = slot0 + slot < total;
-        const u64* bx = stage + (size_t)s * STAGE_U64 + slot * 3;
-        const u64* ba = bx + (size_t)(grp + 1) * CS * 3;
-        u64 x0 = 0, x1 = 0, x2 = 0, a0 = 0, a1 = 0, a2 = 0;
-        if (live) { x0 = bx[0]; x1 = bx[1]; x2 = bx[2]; a0 = ba[0]; a1 = ba[1]; a2 = ba[2]; }
+        mbar_wait(&full[s], phase);
+        const u64* bx = tbase + s * STAGE_U64;
+        const u64* ba = bx + (grp + 1) * ROW_U64;
+        u64 x[SPT][3], a[SPT][3];
+#pragma unroll
+        for (int q = 0; q < SPT; q++) {
+            const bool live = !decltype(ragged)::value || slot + q * CS < last_valid;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                x[q][k] = live ? bx[q * CS * 3 + k] : 0;
+                a[q][k] = live ? ba[q * CS * 3 + k] : 0;
+            }
+        }
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
-        // limbs in memory are canonical, so the weak-form additions are exact residues (a + b with b canonical)
-        const u64 x01 = gl::add(x0, x1), x02 = gl::add(x0, x2), x12 = gl::add(x1, x2);
-        const u64 a01 = gl::add(a0, a1), a02 = gl::add(a0, a2), a12 = gl::add(a1, a2);
-        gl::acc_mad(P0, a0, x0);
-        gl::acc_mad(P1, a1, x1);
-        gl::acc_mad(P2, a2, x2);
-        gl::acc_mad(P01, a01, x01);
-        gl::acc_mad(P02, a02, x02);
-        gl::acc_mad(P12, a12, x12);
+#if defined(SR_GLK_NOCOMPUTE)  // experiment: the data path alone (results are wrong)
+#pragma unroll
+        for (int q = 0; q < SPT; q++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) { P0.e0 ^= (u32)x[q][k] ^ (u32)(a[q][k] >> 32); P0.e1 += (u32)a[q][k]; }
+        return;
+#endif
+#pragma unroll
+        for (int q = 0; q < SPT; q++) {
+            // limbs in memory are canonical, so the weak-form additions are exact residues (a + b, b canonical)
+            const u64 x01 = gl::add_cc(x[q][0], x[q][1]), x02 = gl::add_cc(x[q][0], x[q][2]), x12 = gl::add_cc(x[q][1], x[q][2]);
+            const u64 a01 = gl::add_cc(a[q][0], a[q][1]), a02 = gl::add_cc(a[q][0], a[q][2]), a12 = gl::add_cc(a[q][1], a[q][2]);
+            gl::acc_mad(P0, a[q][0], x[q][0]);
+            gl::acc_mad(P1, a[q][1], x[q][1]);
+            gl::acc_mad(P2, a[q][2], x[q][2]);
+            gl::acc_mad(P01, a01, x01);
+            gl::acc_mad(P02, a02, x02);
+            gl::acc_mad(P12, a12, x12);
+        }
+    };
+    // this CTA's last chunk is ragged iff it is the globally last chunk and that one is short
+    const bool own_ragged = my_chunks > 0 && last_valid != CHUNK &&
+                            blockIdx.x + (unsigned)(my_chunks - 1) * gridDim.x == nchunks - 1;
+    const int full_chunks = my_chunks - (own_ragged ? 1 : 0);
+    uint32_t phase = 0;
+    int it = 0;
+    for (; it + NS <= full_chunks; it += NS, phase ^= 1) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) step(it + s, s, phase, std::false_type());
     }
+    for (int s = 0; it < full_chunks; it++, s++) step(it, s, phase, std::false_type());
+    if (own_ragged) step(it, it % NS, phase, std::true_type());
     __syncthreads();  // every stage has been consumed: `red` may overwrite them
     {
         const u64 p0 = gl::acc_reduce(P0), p1 = gl::acc_reduce(P1), p2 = gl::acc_reduce(P2);
@@ -268,17 +308,18 @@ gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
     mv_tail<S>(tail, nrows, row0, rb, red, sflag);
 }
 
-template <int RB, int NS, int CS>
+template <int RB, int NS, int CS, int SPT>
 static cudaError_t gl_k6_launch(const u64* const* d_rows, size_t nrows, size_t row0, size_t ncols, const u64* v,
                                 const MvTail& tail, int max_grid, cudaStream_t st, int sms) {
-    auto kern = gl_matvec_k6_kernel<RB, NS, CS>;
+    auto kern = gl_matvec_k6_kernel<RB, NS, CS, SPT>;
     const int threads = CS * RB;
-    const size_t smem = (size_t)NS * (RB + 1) * CS * 24 + 2 * NS * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t)NS * (RB + 1) * CS * SPT * 24 + 2 * NS * sizeof(uint64_t) + 16 + 4 * sizeof(void*);
     static KernelCache cache;
     int bps = 0;
     cudaError_t e = cache.configure(kern, threads, smem, &bps);
     if (e != cudaSuccess) return e;
-    const size_t nchunks = (ncols * GLSlot::SLOTS + CS - 1) / CS;
+    const size_t nchunks = (ncols * GLSlot::SLOTS + CS * SPT - 1) / (CS * SPT);
+    if (nchunks >= (1ull << 31)) return cudaErrorInvalidValue;
     size_t grid = (size_t)sms * bps;
     if (grid > (size_t)max_grid) grid = max_grid;
     if (grid > nchunks) grid = nchunks;
@@ -424,6 +465,9 @@ matvec_empty_kernel(size_t nrows, size_t row0, MvTail tail) {
 #ifndef SR_GLK_CS
 #define SR_GLK_CS 128
 #endif
+#ifndef SR_GLK_SPT
+#define SR_GLK_SPT 2
+#endif
 template <class S>
 static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
                                    u64* out, void* scratch, unsigned* counter, cudaStream_t st, int sms, int* launches,
@@ -445,10 +489,10 @@ static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nr
         } else if (ring == RING_GL) {
             const size_t left = nrows - row0;
             const int mg = mv_grid(sms);
-            if (left >= 4) e = gl_k6_launch<4, SR_GLK_NS, SR_GLK_CS>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
-            else if (left == 3) e = gl_k6_launch<3, SR_GLK_NS, SR_GLK_CS>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
-            else if (left == 2) e = gl_k6_launch<2, SR_GLK_NS, SR_GLK_CS>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
-            else e = gl_k6_launch<1, SR_GLK_NS, SR_GLK_CS>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
+            if (left >= 4) e = gl_k6_launch<4, SR_GLK_NS, SR_GLK_CS, SR_GLK_SPT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
+            else if (left == 3) e = gl_k6_launch<3, SR_GLK_NS, SR_GLK_CS, SR_GLK_SPT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
+            else if (left == 2) e = gl_k6_launch<2, SR_GLK_NS, SR_GLK_CS, SR_GLK_SPT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
+            else e = gl_k6_launch<1, SR_GLK_NS, SR_GLK_CS, SR_GLK_SPT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms);
         } else {
             const size_t total = ncols * S::SLOTS;
             int grid = mv_grid(sms);

@@ -115,36 +115,39 @@ class PeerCommit:
         if barrier is not None:
             barrier()  # nobody commits before every rank has the mailbox mapped
 
-    def _product(self, matrix_shard, v_shard, as_rank, out):
+    def _product(self, matrix_shard, v_shard, as_rank, out, ctx=None):
         import ctypes as C
         from . import _lib as L
         from .rings import _ptr_loc
         cfg = self.config
+        ctx = ctx or self.ctx
         pv, nv, loc, dev = _ptr_loc(v_shard.data)
         if loc != L.SR_DEVICE:
             raise ValueError("PeerCommit works on device-resident shards")
         ptrs = (C.c_void_p * max(matrix_shard.nrows, 1))()
         for i, r in enumerate(matrix_shard.vals):
             ptrs[i] = _ptr_loc(r.data)[0]
-        self.ctx.use_torch_stream()
+        ctx.use_torch_stream()
         rank = self.rank if as_rank is None else as_rank
         epoch = 0 if self.device_epochs else self.epoch
         if out is None:
-            rc = L.lib.sr_commit_send(self.ctx.h, cfg.ring_id, ptrs, matrix_shard.nrows, matrix_shard.ncols, pv, nv,
+            rc = L.lib.sr_commit_send(ctx.h, cfg.ring_id, ptrs, matrix_shard.nrows, matrix_shard.ncols, pv, nv,
                                       self.box, rank, epoch)
-            self.ctx.check(rc, "sr_commit_send")
+            ctx.check(rc, "sr_commit_send")
         else:
-            rc = L.lib.sr_commit_root(self.ctx.h, cfg.ring_id, ptrs, matrix_shard.nrows, matrix_shard.ncols, pv, nv,
+            rc = L.lib.sr_commit_root(ctx.h, cfg.ring_id, ptrs, matrix_shard.nrows, matrix_shard.ncols, pv, nv,
                                       self.box, rank, epoch, C.c_void_p(out.data_ptr()))
-            self.ctx.check(rc, "sr_commit_root")
+            ctx.check(rc, "sr_commit_root")
 
-    def send(self, matrix_shard, v_shard, as_rank=None):
-        """This rank's share of the product, written into the root's mailbox (asynchronous)."""
-        self._product(matrix_shard, v_shard, as_rank, None)
+    def send(self, matrix_shard, v_shard, as_rank=None, ctx=None):
+        """This rank's share of the product, written into the root's mailbox (asynchronous).  `ctx`: the context
+        whose scratch / row table the product uses (default: the one given at construction); a caller that commits
+        several resident matrices in turn keeps one context per matrix, so that no row table is re-uploaded."""
+        self._product(matrix_shard, v_shard, as_rank, None, ctx)
 
-    def root_commit(self, matrix_shard, v_shard, out, as_rank=None):
+    def root_commit(self, matrix_shard, v_shard, out, as_rank=None, ctx=None):
         """Root only: the root's share AND the modular sum over all ranks in one kernel (asynchronous)."""
-        self._product(matrix_shard, v_shard, as_rank, out)
+        self._product(matrix_shard, v_shard, as_rank, out, ctx)
         return out
 
     def reduce(self, nrows, out):
@@ -157,19 +160,19 @@ class PeerCommit:
                                               C.c_void_p(out.data_ptr())), "sr_commit_reduce")
         return out
 
-    def commit(self, matrix_shard, v_shard, out=None):
+    def commit(self, matrix_shard, v_shard, out=None, ctx=None):
         """One commitment: every rank calls it with its column shard; returns the result on the root, None elsewhere."""
         import torch
         self.epoch += 1
         if self.rank != self.root:
-            self.send(matrix_shard, v_shard)
+            self.send(matrix_shard, v_shard, ctx=ctx)
             return None
         if out is None:
             out = torch.empty(matrix_shard.nrows * self.config.limbs, dtype=v_shard.data.dtype,
                               device=v_shard.data.device)
         if self.fused:
-            return self.root_commit(matrix_shard, v_shard, out)
-        self.send(matrix_shard, v_shard)
+            return self.root_commit(matrix_shard, v_shard, out, ctx=ctx)
+        self.send(matrix_shard, v_shard, ctx=ctx)
         return self.reduce(matrix_shard.nrows, out)
 
     def timed_out(self) -> bool:

@@ -77,6 +77,12 @@ class Context:
     def kernel_launches(self) -> int:
         return int(L.lib.sr_kernel_launches(self.h))
 
+    def imad_peak(self):
+        """Measured integer multiply-add peaks of this device in 10^12 op/s: (IMAD, IMAD.WIDE.U32, IMAD.WIDE.U32.X)."""
+        t = (ctypes.c_double * 3)()
+        self.check(L.lib.sr_imad_peak(self.h, t), "sr_imad_peak")
+        return float(t[0]), float(t[1]), float(t[2])
+
     def timer_start(self):
         self.check(L.lib.sr_timer_start(self.h), "sr_timer_start")
 
