@@ -453,6 +453,8 @@ def measure_commit(env, tag, kappa, log2m, steps, warmup, path="peer", graph=Tru
     shard_bytes = (kappa * m_local + m_local + kappa) * ELEM_BYTES[tag]
     nsets = max(1, min(8, -(-4 * L2_BYTES // shard_bytes)))  # working set >= 4 x L2
     ctxs = [env.ctx] + [S.Context(env.local) for _ in range(nsets - 1)]
+    for c in ctxs:
+        c.set_pipelined(True)  # resident inputs: the column loop of commitment i + 1 overlaps the tail of commitment i
     sets = []
     for k in range(nsets):
         ctxs[k].use_torch_stream()
@@ -601,6 +603,9 @@ def measure_commit(env, tag, kappa, log2m, steps, warmup, path="peer", graph=Tru
                "root's HBM and publishes a flag; the tail of the root's kernel acquires the flags and adds mod p"
                if peer else "NCCL all_gather of raw limbs + rank-0 modular sum"),
            "cuda_graph": cuda_graph,
+           "pipelined": "programmatic dependent launch: the column loop of a commitment starts while the previous one "
+                        "is in its tail (cross-CTA reduction + NVLink hand-off); chunks are drawn from a device-wide "
+                        "counter so a CTA that starts late draws fewer",
            "l2": "rotating over %d distinct resident shards per rank (%.0f MB each): working set >= 4 x L2" % (
                nsets, shard_bytes / 1e6),
            "product_kernel_us": kernel_ms * 1e3, "step_us": ms * 1e3,
@@ -613,6 +618,7 @@ def measure_commit(env, tag, kappa, log2m, steps, warmup, path="peer", graph=Tru
            "clocks": clocks}
     if peer is not None:
         peer.close()
+    env.ctx.set_pipelined(False)
     return rec
 
 

@@ -56,6 +56,12 @@ const char* sr_version(void);
 int sr_set_stream(sr_ctx* ctx, void* cuda_stream); /* enqueue SR_DEVICE calls on this cudaStream_t (NULL = default stream) */
 int sr_reset_stream(sr_ctx* ctx);                  /* back to the context's own non-blocking stream */
 int sr_sync(sr_ctx* ctx);
+/* Pipelined products (off by default).  When on, the mat-vec / commitment kernels of this context are launched with
+ * programmatic dependent launch: the column loop of a product may start while the previous kernel on the stream is
+ * still in its tail (the cross-CTA reduction and, in a commitment, the NVLink hand-off), which hides that tail in a
+ * sequence of products.  Only the column loop runs early, and it only READS the matrix rows and the vector: turn
+ * this on when those inputs are resident (not written by the kernel enqueued immediately before the product). */
+int sr_set_pipelined(sr_ctx* ctx, int on);
 size_t sr_elem_limbs(int ring);               /* 24 / 72 / 64; 0 for an unknown ring */
 uint64_t sr_kernel_launches(sr_ctx* ctx);     /* kernels launched by this context so far */
 

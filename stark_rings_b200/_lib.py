@@ -39,6 +39,7 @@ _sig("sr_version", ctypes.c_char_p)
 _sig("sr_set_stream", _int, _vp, _vp)
 _sig("sr_reset_stream", _int, _vp)
 _sig("sr_sync", _int, _vp)
+_sig("sr_set_pipelined", _int, _vp, _int)
 _sig("sr_elem_limbs", _sz, _int)
 _sig("sr_kernel_launches", ctypes.c_uint64, _vp)
 _sig("sr_dev_alloc", _int, _vp, _sz, _pp)
@@ -85,7 +86,7 @@ for _tag in ("gl", "bb", "sp"):
 
 # every symbol include/stark_rings_cuda.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "sr_init", "sr_destroy", "sr_last_error", "sr_version", "sr_set_stream", "sr_reset_stream", "sr_sync", "sr_elem_limbs",
+    "sr_init", "sr_destroy", "sr_last_error", "sr_version", "sr_set_stream", "sr_reset_stream", "sr_sync", "sr_set_pipelined", "sr_elem_limbs",
     "sr_kernel_launches", "sr_dev_alloc", "sr_dev_free", "sr_host_alloc", "sr_host_free", "sr_h2d", "sr_d2h",
     "sr_timer_start", "sr_timer_stop", "sr_imad_peak", "sr_crt_batch", "sr_icrt_batch", "sr_ntt_mul_batch", "sr_ring_mul_batch",
     "sr_matvec", "sr_matvec_partial", "sr_modsum_partials", "sr_reduce_batch", "sr_rot_batch",

@@ -21,8 +21,8 @@ cudaError_t sp_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cu
 // scratch (>= matvec_scratch_bytes).  Returns the number of kernels launched via *launches.
 size_t matvec_scratch_bytes(int ring, size_t nrows, int sms);
 cudaError_t matvec_launch(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
-                          u64* out, void* scratch, unsigned* counter, cudaStream_t st, int sms, int* launches,
-                          const PeerSync* ps);
+                          u64* out, void* scratch, unsigned* counters, unsigned* seq, bool pdl, cudaStream_t st, int sms,
+                          int* launches, const PeerSync* ps);
 cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t stride_rows, size_t nrows, u64* out,
                           cudaStream_t st, const PeerSync* ps);
 // coefficient-form helpers (sr_coeff.cu): op 0 = reduce, op 1 = rot
@@ -65,7 +65,9 @@ struct sr_ctx {
     void* mv_rows = nullptr;  // device copy of the row-pointer table
     size_t mv_rows_cap = 0;
     std::vector<const void*> mv_rows_cached;  // host copy of what mv_rows holds (skip re-upload if unchanged)
-    unsigned* commit_counters = nullptr;      // [4] block-arrival tickets: [0] mat-vec tail, [1] mailbox reduction
+    unsigned* commit_counters = nullptr;      // [4]: [0] mat-vec tail ticket, [1] mailbox-reduction ticket, [2..3] chunk counters
+    unsigned mv_seq = 0;                      // mat-vec launches so far (alternates the chunk counter)
+    bool pipelined = false;                   // sr_set_pipelined: successive products may overlap (PDL)
     cudaEvent_t ev_stream = nullptr;          // orders a newly selected stream after the previous one (sr_set_stream)
     std::vector<std::pair<void*, size_t>> pool;  // grow-only device scratch of the host-buffer paths (DevTemps)
     int* dflag = nullptr;                     // device error flag of the checking kernels (allocated once)
@@ -272,7 +274,7 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
             CU(cudaStreamSynchronize(st));
         }
         CU(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, v, out, ctx->mv_scratch,
-                             ctx->commit_counters, st, ctx->sms, &launches, ps));
+                             ctx->commit_counters, &ctx->mv_seq, ctx->pipelined, st, ctx->sms, &launches, ps));
         ctx->launches += launches;
         return SR_OK;
     }
@@ -297,7 +299,7 @@ int matvec_impl(sr_ctx* ctx, int ring, const u64* const* rows, size_t nrows, siz
     ctx->mv_rows_cached.clear();
     CU(cudaMemcpyAsync(ctx->mv_rows, drows.data(), nrows * sizeof(void*), cudaMemcpyHostToDevice, st));
     CU(sr::matvec_launch(ring, (const u64* const*)ctx->mv_rows, nrows, ncols, (const u64*)dv, (u64*)dout,
-                         ctx->mv_scratch, ctx->commit_counters, st, ctx->sms, &launches, nullptr));
+                         ctx->mv_scratch, ctx->commit_counters, &ctx->mv_seq, false, st, ctx->sms, &launches, nullptr));
     ctx->launches += launches;
     CU(cudaMemcpyAsync(out, dout, nrows * w * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -611,6 +613,13 @@ int sr_set_stream(sr_ctx* ctx, void* cuda_stream) {
     if (!ctx) return SR_ERR_INVALID;
     std::lock_guard<std::mutex> lk(ctx->mu);
     return switch_stream(ctx, (cudaStream_t)cuda_stream);  // NULL is CUDA's (legacy) default stream
+}
+
+int sr_set_pipelined(sr_ctx* ctx, int on) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->pipelined = on != 0;
+    return SR_OK;
 }
 
 int sr_reset_stream(sr_ctx* ctx) {

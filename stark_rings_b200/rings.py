@@ -73,6 +73,11 @@ class Context:
             self.check(L.lib.sr_set_stream(self.h, ctypes.c_void_p(s)), "sr_set_stream")
             self._stream = s
 
+    def set_pipelined(self, on: bool = True):
+        """Successive mat-vec / commitment kernels of this context may overlap (programmatic dependent launch): the
+        column loop of a product starts while the previous one is still in its tail.  For resident inputs."""
+        self.check(L.lib.sr_set_pipelined(self.h, 1 if on else 0), "sr_set_pipelined")
+
     @property
     def kernel_launches(self) -> int:
         return int(L.lib.sr_kernel_launches(self.h))

@@ -125,3 +125,32 @@ def test_whole_buffer_batch_ops_2p20(S, name):
     t = da.clone()
     cfg.ntt_mul_batch(t, db)
     assert np.array_equal(host(t), C.ntt_mul(name, a.copy(), b.copy(), threads=T))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_pipelined_products_back_to_back(S, name):
+    """sr_set_pipelined: successive products of one context overlap (the column loop of product i + 1 runs while
+    product i is in its tail; Goldilocks draws its chunks from a device-wide counter).  Twenty products enqueued
+    without any synchronisation, alternating two matrices of different shapes, every output against the oracle."""
+    import torch
+    cfg = S.CONFIGS[name]
+    ctx = S.Context(0)
+    ctx.set_pipelined(True)
+    try:
+        shapes = [(4, 70001), (5, 9000)] if name == "goldilocks" else [(4, 9001), (3, 2000)]
+        mats = []
+        for i, (kappa, m) in enumerate(shapes):
+            rows, v = _inputs(name, kappa, m, 777 + i)
+            want = C.matvec(name, rows, v, threads=kappa)
+            A = S.Matrix([S.RqNTT(cfg, dev(r), ctx) for r in rows], ctx)
+            mats.append((A, S.RqNTT(cfg, dev(v), ctx), want))
+        torch.cuda.synchronize()
+        outs = []
+        for it in range(20):
+            A, v, want = mats[it % 2]
+            outs.append((A.try_mul_vec(v), want))
+        torch.cuda.synchronize()
+        for y, want in outs:
+            assert np.array_equal(host(y.data), want)
+    finally:
+        ctx.close()
