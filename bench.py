@@ -454,7 +454,7 @@ def measure_commit(env, tag, kappa, log2m, steps, warmup, path="peer", graph=Tru
     nsets = max(1, min(8, -(-4 * L2_BYTES // shard_bytes)))  # working set >= 4 x L2
     ctxs = [env.ctx] + [S.Context(env.local) for _ in range(nsets - 1)]
     for c in ctxs:
-        c.set_pipelined(True)  # resident inputs: the column loop of commitment i + 1 overlaps the tail of commitment i
+        c.set_pipelined(not env.args.no_pipeline)  # resident inputs: the column loop of commitment i + 1 overlaps the tail of commitment i
     sets = []
     for k in range(nsets):
         ctxs[k].use_torch_stream()
@@ -640,6 +640,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (the line's `extra` list)")
     ap.add_argument("--commit-path", default="peer", choices=["peer", "nccl"],
                     help="commit workload, N > 1: how the per-rank partials reach rank 0")
+    ap.add_argument("--no-pipeline", action="store_true", help="commit workload: no programmatic dependent launch")
     ap.add_argument("--no-graph", action="store_true", help="commit workload: do not capture the steps in a CUDA graph")
     args = ap.parse_args()
     default_run = args.ring is None and args.log2n is None and args.workload == "ringmul"

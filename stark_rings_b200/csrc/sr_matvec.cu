@@ -58,7 +58,6 @@ struct MvTail {
     u64* partial;       // scratch: [gridDim.x][nrows] partial elements
     u64* out;           // result rows (role 0: nrows elements; role 3: the final sum over all ranks)
     unsigned* counter;  // arrival ticket, zero between launches
-    unsigned* chunk_ctr;  // work counter of this launch (dynamic chunk scheduling), zero between its uses
     int last_pass;      // this launch covers the last rows of the product: publish
     PeerSync ps;
 };
@@ -66,7 +65,9 @@ struct MvTail {
 // Programmatic dependent launch (sm_90+): with the launch attribute set, the CTAs of the NEXT kernel on the stream may
 // start once every CTA of this one has executed launch_dependents (or exited), i.e. while this kernel's last CTA is
 // still in its tail; `wait` blocks until the previous kernel has completed and its writes are visible.  Without the
-// attribute both are no-ops.
+// attribute both are no-ops.  A pipelined launch uses one CTA slot less than the GPU has, so that the slot still
+// held by the previous kernel's tail does not turn one CTA of this kernel into a straggler (the chunks are assigned
+// statically; drawing them from a device-wide counter instead was measured 12% slower).
 SR_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 SR_D void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -124,14 +125,13 @@ SR_D void mv_tail(const MvTail& t, size_t nrows, size_t row0, int rb, typename S
         S::store(dst + (row0 + r) * S::ELEM_U64 + slot * S::SLOT_U64, s);
     }
     if (!mailbox) {
-        if (tid == 0) { *t.counter = 0; *t.chunk_ctr = 0; }  // ready for the next launch on this stream
+        if (tid == 0) *t.counter = 0;  // ready for the next launch on this stream
         return;
     }
     __threadfence_system();  // the result stores (possibly to peer memory) before the flag
     __syncthreads();
     if (tid == 0) {
         *t.counter = 0;
-        *t.chunk_ctr = 0;
         if (t.last_pass && ok) {
             *ps.epoch_ctr = epoch;
             __threadfence_system();
@@ -200,32 +200,18 @@ gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
     uint64_t* empty = full + NS;
     int* sflag = reinterpret_cast<int*>(empty + NS);
     const u64** srow = reinterpret_cast<const u64**>(sflag + 4);  // the RB row pointers (read by the issuing thread)
-    volatile int* snv = reinterpret_cast<volatile int*>(srow + 4);  // [NS] valid slots per stage
     S::Val* red = reinterpret_cast<S::Val*>(smem);  // the stages are dead once the column loop is over
 
     const int slot = threadIdx.x % CS, grp = threadIdx.x / CS;  // row row0 + grp
     const size_t total = ncols * S::SLOTS;
     const unsigned nchunks = (unsigned)((total + CHUNK - 1) / CHUNK);
     const int last_valid = (int)(total - (size_t)(nchunks - 1) * CHUNK);  // slots in the globally last chunk
+    const int my_chunks = (nchunks > blockIdx.x) ? (int)((nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
-    // Chunks are handed out by a device-wide counter (thread 0 draws one per refill): a CTA that starts late -- its SM
-    // was still running the tail of the previous commitment, see pdl_* above -- simply draws fewer.  The arithmetic
-    // is exact, so the result does not depend on which CTA summed which chunk.  snv[s] = valid slots of the chunk in
-    // stage s, 0 = no more chunks (written before the arrival on full[s], read after its completion).
-    bool drained = false;  // thread 0: the counter has run out
-    auto issue = [&](int s) {  // thread 0 only: draw the next chunk into stage s
-        if (drained) return;
-        const unsigned chunk = atomicAdd(tail.chunk_ctr, 1u);
-        if (chunk >= nchunks) {
-            drained = true;
-            snv[s] = 0;
-            mbar_arrive(&full[s]);
-            return;
-        }
+    auto issue = [&](int it, int s) {  // thread 0 only: chunk `it` of this CTA into stage s
+        const unsigned chunk = blockIdx.x + (unsigned)it * gridDim.x;
         const size_t slot0 = (size_t)chunk * CHUNK;
-        const int nv = (chunk == nchunks - 1) ? last_valid : CHUNK;
-        snv[s] = nv;
-        const uint32_t bytes = (uint32_t)nv * 24;
+        const uint32_t bytes = (uint32_t)((chunk == nchunks - 1 ? last_valid : CHUNK) * 24);
         mbar_arrive_expect_tx(&full[s], bytes * (RB + 1));
         u64* dst = stage + (size_t)s * STAGE_U64;
         tma_load_1d(dst, v + slot0 * 3, bytes, &full[s]);
@@ -238,7 +224,7 @@ gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
         for (int r = 0; r < RB; r++) srow[r] = (row0 + r < nrows) ? rows[row0 + r] : rows[nrows - 1];
         for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], RB * CS / 32); }
         mbar_fence_init();
-        for (int s = 0; s < NS; s++) issue(s);
+        for (int it = 0; it < NS && it < my_chunks; it++) issue(it, it);
     }
     __syncthreads();
 
@@ -246,39 +232,28 @@ gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
     gl::acc_zero(P0); gl::acc_zero(P1); gl::acc_zero(P2); gl::acc_zero(P01); gl::acc_zero(P02); gl::acc_zero(P12);
 
     const u64* tbase = stage + slot * 3;  // this thread's first slot of the vector in stage 0
-    // one chunk out of stage s; false when the stage holds the end marker.  Only the globally last chunk may be short
-    // (stale bytes of an earlier chunk sit behind it in the stage): only then are the loads guarded.
-    auto step = [&](bool first, int s, uint32_t phase) -> bool {
-        if (threadIdx.x == 0 && !first) {
+    // one chunk: stage s holds chunk `it` of this CTA.  RAGGED: the globally last chunk may be short (stale bytes of
+    // an earlier chunk sit behind it in the stage): only then are the loads guarded.
+    auto step = [&](int it, int s, uint32_t phase, auto ragged) {
+        if (threadIdx.x == 0 && it > 0 && it - 1 + NS < my_chunks) {
             // refill the stage that was consumed one trip ago (no CTA barrier: the other warps never wait for this
             // one, and this one only waits for warps that lag a whole trip behind)
             const int ps = (s + NS - 1) % NS;
-            if (!drained) {
-                mbar_wait(&empty[ps], s == 0 ? (phase ^ 1) : phase);
-                issue(ps);
-            }
+            mbar_wait(&empty[ps], s == 0 ? (phase ^ 1) : phase);
+            issue(it - 1 + NS, ps);
         }
         __syncwarp();
         mbar_wait(&full[s], phase);
-        const int nv = snv[s];
-        if (nv == 0) return false;
         const u64* bx = tbase + s * STAGE_U64;
         const u64* ba = bx + (grp + 1) * ROW_U64;
         u64 x[SPT][3], a[SPT][3];
-        if (nv == CHUNK) {
 #pragma unroll
-            for (int q = 0; q < SPT; q++)
+        for (int q = 0; q < SPT; q++) {
+            const bool live = !decltype(ragged)::value || slot + q * CS < last_valid;
 #pragma unroll
-                for (int k = 0; k < 3; k++) { x[q][k] = bx[q * CS * 3 + k]; a[q][k] = ba[q * CS * 3 + k]; }
-        } else {
-#pragma unroll
-            for (int q = 0; q < SPT; q++) {
-                const bool live = slot + q * CS < nv;
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    x[q][k] = live ? bx[q * CS * 3 + k] : 0;
-                    a[q][k] = live ? ba[q * CS * 3 + k] : 0;
-                }
+            for (int k = 0; k < 3; k++) {
+                x[q][k] = live ? bx[q * CS * 3 + k] : 0;
+                a[q][k] = live ? ba[q * CS * 3 + k] : 0;
             }
         }
         __syncwarp();
@@ -288,7 +263,7 @@ gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
         for (int q = 0; q < SPT; q++)
 #pragma unroll
             for (int k = 0; k < 3; k++) { P0.e0 ^= (u32)x[q][k] ^ (u32)(a[q][k] >> 32); P0.e1 += (u32)a[q][k]; }
-        return true;
+        return;
 #endif
 #pragma unroll
         for (int q = 0; q < SPT; q++) {
@@ -302,20 +277,19 @@ gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
             gl::acc_mad(P02, a02, x02);
             gl::acc_mad(P12, a12, x12);
         }
-        return true;
     };
-    {
-        uint32_t phase = 0;
-        bool first = true, more = true;
-        while (more) {
+    // this CTA's last chunk is ragged iff it is the globally last chunk and that one is short
+    const bool own_ragged = my_chunks > 0 && last_valid != CHUNK &&
+                            blockIdx.x + (unsigned)(my_chunks - 1) * gridDim.x == nchunks - 1;
+    const int full_chunks = my_chunks - (own_ragged ? 1 : 0);
+    uint32_t phase = 0;
+    int it = 0;
+    for (; it + NS <= full_chunks; it += NS, phase ^= 1) {
 #pragma unroll
-            for (int s = 0; s < NS; s++) {
-                if (more) more = step(first, s, phase);
-                first = false;
-            }
-            phase ^= 1;
-        }
+        for (int s = 0; s < NS; s++) step(it + s, s, phase, std::false_type());
     }
+    for (int s = 0; it < full_chunks; it++, s++) step(it, s, phase, std::false_type());
+    if (own_ragged) step(it, it % NS, phase, std::true_type());
     // the column loop is over: the next kernel on the stream may start its own (its tail will wait for ours)
     pdl_wait();
     pdl_launch_dependents();
@@ -368,7 +342,7 @@ static cudaError_t gl_k6_launch(const u64* const* d_rows, size_t nrows, size_t r
                                 const MvTail& tail, int max_grid, cudaStream_t st, int sms, bool pdl) {
     auto kern = gl_matvec_k6_kernel<RB, NS, CS, SPT>;
     const int threads = CS * RB;
-    const size_t smem = (size_t)NS * (RB + 1) * CS * SPT * 24 + 2 * NS * sizeof(uint64_t) + 16 + 4 * sizeof(void*) + NS * sizeof(int);
+    const size_t smem = (size_t)NS * (RB + 1) * CS * SPT * 24 + 2 * NS * sizeof(uint64_t) + 16 + 4 * sizeof(void*);
     static KernelCache cache;
     int bps = 0;
     cudaError_t e = cache.configure(kern, threads, smem, &bps);
@@ -377,6 +351,7 @@ static cudaError_t gl_k6_launch(const u64* const* d_rows, size_t nrows, size_t r
     if (nchunks >= (1ull << 31)) return cudaErrorInvalidValue;
     size_t grid = (size_t)sms * bps;
     if (grid > (size_t)max_grid) grid = max_grid;
+    if (pdl && grid > 1) grid -= 1;  // the slot the previous kernel's tail may still hold
     if (grid > nchunks) grid = nchunks;
     return launch_pdl(kern, (unsigned)grid, (unsigned)threads, smem, st, pdl, d_rows, nrows, row0, ncols, v, tail);
 }
@@ -526,8 +501,6 @@ matvec_empty_kernel(size_t nrows, size_t row0, MvTail tail) {
 #ifndef SR_GLK_SPT
 #define SR_GLK_SPT 2
 #endif
-// counters: [0] arrival ticket, [2], [3] chunk counters used by alternate launches (a kernel that overlaps the tail of
-// its predecessor must not draw from the counter that tail is about to reset); *seq counts the launches of the context.
 template <class S>
 static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
                                    u64* out, void* scratch, unsigned* counters, unsigned* seq, bool pdl,
@@ -542,7 +515,7 @@ static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nr
     constexpr int RB = SR_MV_RB;
     for (size_t row0 = 0; row0 < nrows; row0 += RB) {
         tail.last_pass = (row0 + RB >= nrows) ? 1 : 0;
-        tail.chunk_ctr = counters + 2 + ((*seq)++ & 1);
+        (*seq)++;
         cudaError_t e = cudaSuccess;
         if (ncols == 0) {
             e = launch_pdl(matvec_empty_kernel<S>, 1u, (unsigned)MV_T, 0, st, pdl, nrows, row0, tail);

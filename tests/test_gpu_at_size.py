@@ -130,7 +130,7 @@ def test_whole_buffer_batch_ops_2p20(S, name):
 @pytest.mark.parametrize("name", ALL)
 def test_pipelined_products_back_to_back(S, name):
     """sr_set_pipelined: successive products of one context overlap (the column loop of product i + 1 runs while
-    product i is in its tail; Goldilocks draws its chunks from a device-wide counter).  Twenty products enqueued
+    product i is in its tail).  Twenty products enqueued
     without any synchronisation, alternating two matrices of different shapes, every output against the oracle."""
     import torch
     cfg = S.CONFIGS[name]
