@@ -237,7 +237,9 @@ gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
     auto step = [&](int it, int s, uint32_t phase, auto ragged) {
         if (threadIdx.x == 0 && it > 0 && it - 1 + NS < my_chunks) {
             // refill the stage that was consumed one trip ago (no CTA barrier: the other warps never wait for this
-            // one, and this one only waits for warps that lag a whole trip behind)
+            // one, and this one only waits for warps that lag a whole trip behind).  (Rotating the refill over the
+            // warps, to spread its ~90 instructions, was measured 50% SLOWER: a refill issued by whichever warp
+            // happens to lag arrives late for everybody.)
             const int ps = (s + NS - 1) % NS;
             mbar_wait(&empty[ps], s == 0 ? (phase ^ 1) : phase);
             issue(it - 1 + NS, ps);
