@@ -96,6 +96,16 @@ int sr_icrt_batch(sr_ctx* ctx, int ring, uint64_t* buf, size_t n_limbs, int loc)
  *           (ntt_form.rs:159-189, 213-225, 521-550): a[i] <- a[i] * b[i] slot-wise, NTT form. */
 int sr_ntt_mul_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, const uint64_t* b, size_t n_limbs, int loc);
 
+/* Replaces  Add / AddAssign / Sub / SubAssign / Neg / Sum for CyclotomicPolyRingNTTGeneral (ntt_form.rs:588-601,
+ *           603-626, 640-654) and the same operators of CyclotomicPolyRingGeneral (coeff_form.rs): both forms add field
+ *           element by field element, so these serve RqPoly and RqNTT batches alike.
+ * a[i] <- a[i] + b[i] / a[i] - b[i] / -a[i] in place; sr_sum_batch folds n elements into one (`out`: one element,
+ * ZERO for an empty slice). */
+int sr_add_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, const uint64_t* b, size_t n_limbs, int loc);
+int sr_sub_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, const uint64_t* b, size_t n_limbs, int loc);
+int sr_neg_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, size_t n_limbs, int loc);
+int sr_sum_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint64_t* out, int loc);
+
 /* Replaces  Mul for CyclotomicPolyRingGeneral (coeff_form.rs:54-67, 250-258): out[i] = a[i] * b[i]
  * in F_p[X]/Phi, coefficient form in and out; computed as icrt(crt(a) * crt(b)) in one kernel
  * (the identity the reference pins in test_mul_crt, e.g. goldilocks/mod.rs:231-247).
@@ -197,6 +207,24 @@ int sr_gadget_recompose(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limb
 int sr_sparse_matvec(sr_ctx* ctx, int ring, size_t nrows, size_t ncols, const uint64_t* row_ptr,
                      const uint64_t* col_idx, const uint64_t* vals, const uint64_t* v, size_t v_limbs, uint64_t* out,
                      int loc);
+
+/* Sparse x sparse product: SparseMatrix<R>::checked_mul_mat / try_mul_mat / Mul<&SparseMatrix<R>> with R = RqNTT
+ * (sparse_matrix.rs:219-275), in two phases.  sr_sparse_matmat_symbolic (host only, no context: indices are host
+ * metadata) is the reference's own structure pass: the columns of M gathered in row order and, for every (row i of A,
+ * column j of M), the merge join of the two index lists in their stored order.  Call it once with the output arrays
+ * NULL to size them (*ncand candidates, *npairs matches), then again to fill cand_row / cand_col [ncand],
+ * pair_ptr [ncand + 1], pair_a / pair_m [npairs] (entry numbers into A's and M's vals).  sr_sparse_matmat_values is
+ * the arithmetic: out_vals[c] = the sum of candidate c's products, nonzero_host[c] = 1 iff one of them is not the zero
+ * element; the reference keeps exactly the candidates with nonzero = 1, in (row, column) order (:249-262).  a_vals,
+ * m_vals and out_vals live in `loc`; the pair arrays and nonzero_host are host arrays.  Synchronous.
+ * A column index of M that is >= m_ncols returns SR_ERR_INVALID (the reference panics). */
+int sr_sparse_matmat_symbolic(size_t a_nrows, const uint64_t* a_row_ptr, const uint64_t* a_col_idx, size_t m_nrows,
+                              size_t m_ncols, const uint64_t* m_row_ptr, const uint64_t* m_col_idx, size_t* ncand,
+                              size_t* npairs, uint64_t* cand_row, uint64_t* cand_col, uint64_t* pair_ptr,
+                              uint64_t* pair_a, uint64_t* pair_m);
+int sr_sparse_matmat_values(sr_ctx* ctx, int ring, const uint64_t* a_vals, const uint64_t* m_vals, size_t ncand,
+                            const uint64_t* pair_ptr, const uint64_t* pair_a, const uint64_t* pair_m,
+                            uint64_t* out_vals, int* nonzero_host, int loc);
 
 /* sr_matmat replaces Matrix<R>::checked_mul_mat / try_mul_mat / Mul<&Matrix<R>> with R = RqNTT
  * (linear_algebra/src/matrix.rs:148-166, 185-197): out[i][j] = sum_k a[i][k] * m[k][j].  a_rows / m_rows / out_rows

@@ -38,6 +38,10 @@ def _bind(path):
     L.sro_matmat.argtypes = [ctypes.c_int, ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t,
                              ctypes.POINTER(u64p), ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(u64p)]
     L.sro_matmat.restype = ctypes.c_int
+    L.sro_addsub.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, ctypes.c_size_t]
+    L.sro_addsub.restype = None
+    L.sro_sum.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, u64p]
+    L.sro_sum.restype = None
     L.sro_scale.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, u64p]
     L.sro_scale.restype = None
     u8p = ctypes.POINTER(ctypes.c_uint8)
@@ -104,6 +108,20 @@ def ntt_mul(ring, a, b, threads=1, L=None):
 def ring_mul(ring, a, b, threads=1, L=None):
     out = np.empty_like(a)
     (L or lib()).sro_ring_mul(RINGS[ring], _p(a), _p(b), _p(out), a.size // words(ring), threads)
+    return out
+
+
+def addsub(ring, op, a, b=None, L=None):
+    """op 'add' / 'sub' / 'neg' element-wise over the batch; returns a new array."""
+    out = a.copy()
+    code = {"add": 0, "sub": 1, "neg": 2}[op]
+    (L or lib()).sro_addsub(RINGS[ring], code, _p(out), _p(b if b is not None else out), out.size // words(ring))
+    return out
+
+
+def ring_sum(ring, a, L=None):
+    out = np.zeros(words(ring), dtype=np.uint64)
+    (L or lib()).sro_sum(RINGS[ring], _p(a), a.size // words(ring), _p(out))
     return out
 
 

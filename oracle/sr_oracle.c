@@ -483,6 +483,33 @@ int sro_matmat(int ring, const u64* const* a_rows, size_t a_nrows, size_t a_ncol
     return 0;
 }
 /* MulAssign<&R> on a batch (matrix.rs:207-211, sparse_matrix.rs:298-302): a[e] *= r */
+/* Element-wise ring addition / subtraction / negation over n elements (ntt_form.rs:588-626 and the same operators of
+ * coeff_form.rs: field element by field element in either form); op 0 = add, 1 = sub, 2 = neg; in place on a. */
+void sro_addsub(int ring, int op, u64* a, const u64* b, size_t n) {
+    pthread_once(&once, init_all);
+    size_t w = sro_elem_words(ring);
+    if (ring == SRO_SP) {
+        fp4 zero = {{0, 0, 0, 0}};
+        for (size_t i = 0; i < n * 16; i++) {
+            fp4* x = (fp4*)a + i;
+            if (op == 0) sp_add(x, x, (const fp4*)b + i);
+            else if (op == 1) sp_sub(x, x, (const fp4*)b + i);
+            else sp_sub(x, &zero, x);
+        }
+        return;
+    }
+    const f1_ctx* F = ring == SRO_GL ? &GL : &BB;
+    for (size_t i = 0; i < n * w; i++)
+        a[i] = op == 0 ? f1_add(F, a[i], b[i]) : op == 1 ? f1_sub(F, a[i], b[i]) : f1_neg(F, a[i]);
+}
+/* Sum of n elements folded from ZERO (ntt_form.rs:640-654) */
+void sro_sum(int ring, const u64* in, size_t n, u64* out) {
+    pthread_once(&once, init_all);
+    size_t w = sro_elem_words(ring);
+    memset(out, 0, w * 8);
+    for (size_t e = 0; e < n; e++) nttadd1(ring, out, in + e * w);
+}
+
 void sro_scale(int ring, u64* a, size_t n, const u64* r) {
     pthread_once(&once, init_all);
     size_t w = sro_elem_words(ring);

@@ -55,6 +55,10 @@ _sig("sr_crt_batch", _int, _vp, _int, _vp, _sz, _int)
 _sig("sr_icrt_batch", _int, _vp, _int, _vp, _sz, _int)
 _sig("sr_ntt_mul_batch", _int, _vp, _int, _vp, _vp, _sz, _int)
 _sig("sr_ring_mul_batch", _int, _vp, _int, _vp, _vp, _vp, _sz, _int)
+_sig("sr_add_batch", _int, _vp, _int, _vp, _vp, _sz, _int)
+_sig("sr_sub_batch", _int, _vp, _int, _vp, _vp, _sz, _int)
+_sig("sr_neg_batch", _int, _vp, _int, _vp, _sz, _int)
+_sig("sr_sum_batch", _int, _vp, _int, _vp, _sz, _vp, _int)
 _sig("sr_matvec", _int, _vp, _int, _pp, _sz, _sz, _vp, _sz, _vp, _int)
 _sig("sr_matvec_partial", _int, _vp, _int, _pp, _sz, _sz, _vp, _sz, _vp, _int)
 _sig("sr_modsum_partials", _int, _vp, _int, _vp, _sz, _sz, _vp, _int)
@@ -63,6 +67,10 @@ _sig("sr_rot_batch", _int, _vp, _int, _vp, _vp, _sz, _int)
 _sig("sr_gadget_decompose", _int, _vp, _int, _vp, _sz, ctypes.c_uint64, ctypes.c_uint64, _sz, _vp, _int)
 _sig("sr_gadget_recompose", _int, _vp, _int, _vp, _sz, ctypes.c_uint64, ctypes.c_uint64, _sz, _vp, _int)
 _sig("sr_sparse_matvec", _int, _vp, _int, _sz, _sz, _vp, _vp, _vp, _vp, _sz, _vp, _int)
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_szp = ctypes.POINTER(ctypes.c_size_t)
+_sig("sr_sparse_matmat_symbolic", _int, _sz, _vp, _vp, _sz, _sz, _vp, _vp, _szp, _szp, _vp, _vp, _vp, _vp, _vp)
+_sig("sr_sparse_matmat_values", _int, _vp, _int, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _int)
 _sig("sr_matmat", _int, _vp, _int, _pp, _sz, _sz, _pp, _sz, _sz, _pp, _int)
 _sig("sr_ntt_scale_batch", _int, _vp, _int, _vp, _sz, _vp, _int)
 _sig("sr_mailbox_create", _int, _vp, _int, _sz, _int, _pp, ctypes.c_char_p)
@@ -89,8 +97,9 @@ EXPORTS = [
     "sr_init", "sr_destroy", "sr_last_error", "sr_version", "sr_set_stream", "sr_reset_stream", "sr_sync", "sr_set_pipelined", "sr_elem_limbs",
     "sr_kernel_launches", "sr_dev_alloc", "sr_dev_free", "sr_host_alloc", "sr_host_free", "sr_h2d", "sr_d2h",
     "sr_timer_start", "sr_timer_stop", "sr_imad_peak", "sr_crt_batch", "sr_icrt_batch", "sr_ntt_mul_batch", "sr_ring_mul_batch",
+    "sr_add_batch", "sr_sub_batch", "sr_neg_batch", "sr_sum_batch",
     "sr_matvec", "sr_matvec_partial", "sr_modsum_partials", "sr_reduce_batch", "sr_rot_batch",
-    "sr_gadget_decompose", "sr_gadget_recompose", "sr_sparse_matvec", "sr_matmat", "sr_ntt_scale_batch",
+    "sr_gadget_decompose", "sr_gadget_recompose", "sr_sparse_matvec", "sr_sparse_matmat_symbolic", "sr_sparse_matmat_values", "sr_matmat", "sr_ntt_scale_batch",
     "sr_mailbox_create", "sr_mailbox_open", "sr_mailbox_destroy", "sr_mailbox_error", "sr_mailbox_set_timeout", "sr_commit_send", "sr_commit_root",
     "sr_commit_reduce",
     "sr_serialized_bytes", "sr_serialize_batch", "sr_deserialize_batch",

@@ -27,6 +27,8 @@ cudaError_t modsum_launch(int ring, const u64* gathered, size_t nranks, size_t s
                           cudaStream_t st, const PeerSync* ps);
 // coefficient-form helpers (sr_coeff.cu): op 0 = reduce, op 1 = rot
 cudaError_t coeff_launch(int ring, int op, const u64* in, u64* out, size_t n, int len, cudaStream_t st);
+// element-wise add / sub / neg (sr_coeff.cu): op 0 = add, 1 = sub, 2 = neg
+cudaError_t addsub_launch(int ring, int op, u64* a, const u64* b, size_t n, cudaStream_t st);
 // balanced gadget decomposition / recomposition (sr_decomp.cu): op 0 = decompose, op 1 = recompose
 cudaError_t decomp_launch(int ring, int op, const u64* in, u64* out, size_t n, unsigned long long b, u64 b_std, int pad,
                           int* overflow, cudaStream_t st);
@@ -36,6 +38,8 @@ cudaError_t sparse_matvec_launch(int ring, const u64* row_ptr, const u64* col_id
 cudaError_t matmat_launch(int ring, const u64* const* a_rows, const u64* const* m_rows, u64* const* out_rows,
                           size_t a_nrows, size_t inner, size_t m_ncols, cudaStream_t st);
 cudaError_t scale_launch(int ring, u64* a, const u64* r, size_t n, cudaStream_t st);
+cudaError_t sparse_pairs_launch(int ring, const u64* a_vals, const u64* m_vals, const u64* pair_ptr, const u64* pair_a,
+                                const u64* pair_m, size_t ncand, u64* out, int* nonzero, cudaStream_t st);
 // canonical (de)serialization (sr_serial.cu): op 0 limbs -> bytes, op 1 bytes -> limbs
 cudaError_t serial_launch(int ring, int op, const void* in, void* out, size_t nfe, int* bad, cudaStream_t st);
 // integer multiply-add peaks of the device (sr_peak.cu)
@@ -390,6 +394,7 @@ int sparse_matvec_impl(sr_ctx* ctx, int ring, size_t nrows, size_t ncols, const 
     int bad = 0;
     rcf = flag_end(ctx, st, &bad);
     if (rcf) return rcf;
+    if (bad == 2) return fail(ctx, SR_ERR_INVALID, "row_ptr must be non-decreasing and end at nnz");
     if (bad) return fail(ctx, SR_ERR_INVALID, "column index out of range (the reference panics on v[i])");
     return SR_OK;
 }
@@ -404,6 +409,8 @@ int matmat_impl(sr_ctx* ctx, int ring, const u64* const* a_rows, size_t a_nrows,
         return fail(ctx, SR_ERR_BAD_LENGTH,
                     "DifferentLengths(" + std::to_string(a_ncols) + ", " + std::to_string(m_nrows) + ")");
     if (a_nrows == 0 || m_ncols == 0) return SR_OK;
+    if (a_ncols >= ((size_t)1 << 30))  // the unreduced 160-bit Goldilocks sums hold 2^32 products
+        return fail(ctx, SR_ERR_INVALID, "inner dimension must be below 2^30");
     if (!a_rows || !out_rows || (m_nrows && !m_rows)) return fail(ctx, SR_ERR_INVALID, "null row table");
     if (loc != SR_DEVICE && loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
     for (size_t i = 0; i < a_nrows; i++)
@@ -794,6 +801,62 @@ static int coeff_impl(sr_ctx* ctx, int ring, int op, const uint64_t* in, size_t 
     return SR_OK;
 }
 
+static int addsub_impl(sr_ctx* ctx, int ring, int op, uint64_t* a, const uint64_t* b, size_t n_limbs, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (n_limbs % w != 0) return fail(ctx, SR_ERR_BAD_LENGTH, "slice length is not a whole number of elements");
+    const size_t n = n_limbs / w;
+    if (n == 0) return SR_OK;
+    if (!a || (op != 2 && !b)) return fail(ctx, SR_ERR_INVALID, "null buffer");
+    CU(cudaSetDevice(ctx->device));
+    if (loc == SR_DEVICE) {
+        if (!aligned16(a) || (op != 2 && !aligned16(b)))
+            return fail(ctx, SR_ERR_INVALID, "device buffers must be 16-byte aligned");
+        CU(sr::addsub_launch(ring, op, a, b, n, ctx->stream));
+        ctx->launches++;
+        return SR_OK;
+    }
+    if (loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    cudaStream_t st = ctx->own_stream;
+    DevTemps tmp(ctx);
+    u64 *da = nullptr, *db = nullptr;
+    CU(tmp.upload((void**)&da, a, n_limbs * 8, st));
+    if (op != 2) CU(tmp.upload((void**)&db, b, n_limbs * 8, st));
+    CU(sr::addsub_launch(ring, op, da, db, n, st));
+    ctx->launches++;
+    CU(cudaMemcpyAsync(a, da, n_limbs * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SR_OK;
+}
+int sr_add_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, const uint64_t* b, size_t n_limbs, int loc) {
+    return addsub_impl(ctx, ring, 0, a_inout, b, n_limbs, loc);
+}
+int sr_sub_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, const uint64_t* b, size_t n_limbs, int loc) {
+    return addsub_impl(ctx, ring, 1, a_inout, b, n_limbs, loc);
+}
+int sr_neg_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, size_t n_limbs, int loc) {
+    return addsub_impl(ctx, ring, 2, a_inout, nullptr, n_limbs, loc);
+}
+// Sum of a slice of ring elements (ntt_form.rs:640-654: fold from ZERO with Add): the modular sum kernel of the
+// column-sharded commitment with one "row" and n "ranks".
+int sr_sum_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t n_limbs, uint64_t* out, int loc) {
+    const size_t w = elem_limbs(ring);
+    if (!ctx) return SR_ERR_INVALID;
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (n_limbs % w != 0) return fail(ctx, SR_ERR_BAD_LENGTH, "slice length is not a whole number of elements");
+    if (!out) return fail(ctx, SR_ERR_INVALID, "null buffer");
+    if (n_limbs == 0) {  // Sum of nothing = ZERO
+        if (loc == SR_HOST) { memset(out, 0, w * 8); return SR_OK; }
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        CU(cudaSetDevice(ctx->device));
+        CU(cudaMemsetAsync(out, 0, w * 8, ctx->stream));
+        return SR_OK;
+    }
+    return sr_modsum_partials(ctx, ring, in, n_limbs / w, 1, out, loc);
+}
+
 int sr_reduce_batch(sr_ctx* ctx, int ring, const uint64_t* in, size_t in_limbs, size_t coeffs_per_poly, uint64_t* out,
                     int loc) {
     return coeff_impl(ctx, ring, 0, in, in_limbs, coeffs_per_poly, out, loc);
@@ -863,6 +926,106 @@ int sr_matmat(sr_ctx* ctx, int ring, const uint64_t* const* a_rows, size_t a_nro
 }
 int sr_ntt_scale_batch(sr_ctx* ctx, int ring, uint64_t* a_inout, size_t n_limbs, const uint64_t* r, int loc) {
     return scale_impl(ctx, ring, a_inout, n_limbs, r, loc);
+}
+
+/* ---- sparse x sparse product (SparseMatrix::checked_mul_mat, sparse_matrix.rs:219-275) ---------------------------
+ * Symbolic phase on the host, exactly the reference's: the columns of M are gathered in row order (:224-229), and for
+ * every (row i of A, column j of M) the two index lists are merge-joined in their STORED order (:235-262; sorted
+ * lists pair equal indices, unsorted ones skip entries just as the reference does).  Every (i, j) with at least one
+ * match is a candidate; whether it becomes an entry is decided by the values (a match whose product is the zero
+ * element does not count, :249-256), i.e. by the numeric phase. */
+int sr_sparse_matmat_symbolic(size_t a_nrows, const uint64_t* a_row_ptr, const uint64_t* a_col_idx, size_t m_nrows,
+                              size_t m_ncols, const uint64_t* m_row_ptr, const uint64_t* m_col_idx, size_t* ncand,
+                              size_t* npairs, uint64_t* cand_row, uint64_t* cand_col, uint64_t* pair_ptr,
+                              uint64_t* pair_a, uint64_t* pair_m) {
+    if (!a_row_ptr || !m_row_ptr || !ncand || !npairs) return SR_ERR_INVALID;
+    const size_t a_nnz = a_row_ptr[a_nrows], m_nnz = m_row_ptr[m_nrows];
+    if ((a_nnz && !a_col_idx) || (m_nnz && !m_col_idx)) return SR_ERR_INVALID;
+    // m_cols[j] = entries of column j in row order, as (entry index, row index)
+    std::vector<std::vector<std::pair<uint64_t, uint64_t>>> m_cols(m_ncols);
+    for (size_t r = 0; r < m_nrows; r++) {
+        if (m_row_ptr[r] > m_row_ptr[r + 1]) return SR_ERR_INVALID;
+        for (uint64_t e = m_row_ptr[r]; e < m_row_ptr[r + 1]; e++) {
+            if (m_col_idx[e] >= m_ncols) return SR_ERR_INVALID;  // the reference panics on m_cols[*col_idx]
+            m_cols[m_col_idx[e]].push_back(std::make_pair(e, (uint64_t)r));
+        }
+    }
+    const bool fill = cand_row && cand_col && pair_ptr && pair_a && pair_m;
+    size_t nc = 0, np = 0;
+    for (size_t i = 0; i < a_nrows; i++) {
+        if (a_row_ptr[i] > a_row_ptr[i + 1]) return SR_ERR_INVALID;
+        for (size_t j = 0; j < m_ncols; j++) {
+            const auto& col = m_cols[j];
+            uint64_t ra = a_row_ptr[i];
+            size_t ci = 0;
+            const size_t np0 = np;
+            while (ra < a_row_ptr[i + 1] && ci < col.size()) {
+                const uint64_t r_idx = a_col_idx[ra], c_idx = col[ci].second;
+                if (r_idx < c_idx) ra++;
+                else if (r_idx > c_idx) ci++;
+                else {
+                    if (fill) { pair_a[np] = ra; pair_m[np] = col[ci].first; }
+                    np++;
+                    ra++;
+                    ci++;
+                }
+            }
+            if (np > np0) {
+                if (fill) { cand_row[nc] = i; cand_col[nc] = j; pair_ptr[nc] = np0; }
+                nc++;
+            }
+        }
+    }
+    if (fill) pair_ptr[nc] = np;
+    *ncand = nc;
+    *npairs = np;
+    return SR_OK;
+}
+
+/* Numeric phase: out_vals[c] = sum over the candidate's pairs of a_vals[pair_a] * m_vals[pair_m];
+ * nonzero[c] = 1 iff some product is not the zero element (host array, always). */
+int sr_sparse_matmat_values(sr_ctx* ctx, int ring, const uint64_t* a_vals, const uint64_t* m_vals, size_t ncand,
+                            const uint64_t* pair_ptr, const uint64_t* pair_a, const uint64_t* pair_m,
+                            uint64_t* out_vals, int* nonzero_host, int loc) {
+    if (!ctx) return SR_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = elem_limbs(ring);
+    if (w == 0) return fail(ctx, SR_ERR_INVALID, "unknown ring id");
+    if (ncand == 0) return SR_OK;
+    if (!a_vals || !m_vals || !pair_ptr || !pair_a || !pair_m || !out_vals || !nonzero_host)
+        return fail(ctx, SR_ERR_INVALID, "null buffer");
+    if (loc != SR_DEVICE && loc != SR_HOST) return fail(ctx, SR_ERR_INVALID, "unknown loc");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (loc == SR_DEVICE) ? ctx->stream : ctx->own_stream;
+    const size_t npairs = (size_t)pair_ptr[ncand];  // the index arrays are host arrays in both modes
+    DevTemps tmp(ctx);
+    u64 *d_pp = nullptr, *d_pa = nullptr, *d_pm = nullptr;
+    int* d_nz = nullptr;
+    CU(tmp.upload((void**)&d_pp, pair_ptr, (ncand + 1) * 8, st));
+    CU(tmp.upload((void**)&d_pa, pair_a, npairs * 8, st));
+    CU(tmp.upload((void**)&d_pm, pair_m, npairs * 8, st));
+    CU(tmp.alloc((void**)&d_nz, ncand * sizeof(int)));
+    CU(cudaMemsetAsync(d_nz, 0, ncand * sizeof(int), st));
+    const u64 *k_a = a_vals, *k_m = m_vals;
+    u64* k_out = out_vals;
+    if (loc == SR_HOST) {
+        size_t na = 0, nm = 0;
+        for (size_t e = 0; e < npairs; e++) {
+            if (pair_a[e] + 1 > na) na = pair_a[e] + 1;
+            if (pair_m[e] + 1 > nm) nm = pair_m[e] + 1;
+        }
+        CU(tmp.upload((void**)&k_a, a_vals, na * w * 8, st));
+        CU(tmp.upload((void**)&k_m, m_vals, nm * w * 8, st));
+        CU(tmp.alloc((void**)&k_out, ncand * w * 8));
+    } else if (!aligned16(a_vals) || !aligned16(m_vals) || !aligned16(out_vals)) {
+        return fail(ctx, SR_ERR_INVALID, "device buffers must be 16-byte aligned");
+    }
+    CU(sr::sparse_pairs_launch(ring, k_a, k_m, d_pp, d_pa, d_pm, ncand, k_out, d_nz, st));
+    ctx->launches++;
+    if (loc == SR_HOST) CU(cudaMemcpyAsync(out_vals, k_out, ncand * w * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(nonzero_host, d_nz, ncand * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return SR_OK;
 }
 
 /* ---- mailbox: column-sharded commitment over NVLink peer memory -------------------------------------------- */

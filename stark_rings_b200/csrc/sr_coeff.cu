@@ -110,6 +110,43 @@ rot_kernel(const u64* __restrict__ in, u64* __restrict__ out, size_t n) {
   }
 }
 
+// Element-wise ring addition / subtraction / negation (ntt_form.rs:588-601 Add, :603-626 Sub / Neg, and the same
+// operator impls of coeff_form.rs: both forms add field element by field element, so one kernel serves RqPoly and
+// RqNTT): a[i] <- a[i] + b[i] (op 0), a[i] - b[i] (op 1), -a[i] (op 2).  One thread per field element, FE_PER_THREAD
+// of them a block width apart: pure streaming, 3 S (add / sub) or 2 S (neg) bytes per element.
+template <class F>
+__global__ void __launch_bounds__(256)
+addsub_kernel(u64* __restrict__ a, const u64* __restrict__ b, size_t nfe, int op) {
+#pragma unroll
+    for (int rep = 0; rep < COEFF_PER_THREAD; rep++) {
+        const size_t idx = ((size_t)blockIdx.x * COEFF_PER_THREAD + rep) * 256 + threadIdx.x;
+        if (idx >= nfe) return;
+        const typename F::V x = F::load(a + idx * F::N);
+        typename F::V r;
+        if (op == 0) r = F::add(x, F::load(b + idx * F::N));
+        else if (op == 1) r = F::sub(x, F::load(b + idx * F::N));
+        else r = F::sub(F::zero(), x);
+        F::store(a + idx * F::N, r);
+    }
+}
+template <class F>
+static cudaError_t addsub_launch_t(int op, u64* a, const u64* b, size_t n, cudaStream_t st) {
+    const size_t total = n * F::D;
+    if (total == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((total + 256 * COEFF_PER_THREAD - 1) / (256 * COEFF_PER_THREAD));
+    addsub_kernel<F><<<grid, 256, 0, st>>>(a, b, total, op);
+    return cudaGetLastError();
+}
+// op 0 = add, 1 = sub, 2 = neg (b unused); n ring elements, in place on a
+cudaError_t addsub_launch(int ring, int op, u64* a, const u64* b, size_t n, cudaStream_t st) {
+    switch (ring) {
+    case RING_GL: return addsub_launch_t<GLF>(op, a, b, n, st);
+    case RING_BB: return addsub_launch_t<BBF>(op, a, b, n, st);
+    case RING_SP: return addsub_launch_t<SPF>(op, a, b, n, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <class F>
 static cudaError_t coeff_launch_t(int op, const u64* in, u64* out, size_t n, int len, cudaStream_t st) {
     const size_t total = n * F::D;

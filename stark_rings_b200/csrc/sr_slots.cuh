@@ -18,6 +18,7 @@ struct GLSlot {
     SR_D static void store(u64* p, const Val& v) { p[0] = v.c[0]; p[1] = v.c[1]; p[2] = v.c[2]; }
     SR_D static void store_poison(u64* p) { p[0] = p[1] = p[2] = ~0ull; }
     SR_D static Val zero() { Val v; v.c[0] = v.c[1] = v.c[2] = 0; return v; }
+    SR_D static bool is_zero(const Val& v) { return (v.c[0] | v.c[1] | v.c[2]) == 0; }
     // gl:: arithmetic is weak-form (gl_ring.cuh); values stored in Val are kept canonical
     SR_D static Val mul(const Val& a, const Val& b) {
         Val z;
@@ -92,6 +93,12 @@ struct BBSlot {
         for (int i = 0; i < 9; i++) v.c[i] = 0;
         return v;
     }
+    SR_D static bool is_zero(const Val& v) {
+        u32 o = 0;
+#pragma unroll
+        for (int i = 0; i < 9; i++) o |= v.c[i];
+        return o == 0;
+    }
     SR_D static Val mul(const Val& a, const Val& b) { Val z; bb::slot_mul_ntt(z.c, a.c, b.c); return z; }
     SR_D static void acc(Val& s, const Val& x) {
 #pragma unroll
@@ -142,6 +149,12 @@ struct SPSlot {
 #pragma unroll
         for (int i = 0; i < 8; i++) v.v[i] = 0;
         return v;
+    }
+    SR_D static bool is_zero(const Val& v) {
+        u32 o = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o |= v.v[i];
+        return o == 0;
     }
     SR_D static Val mul(const Val& a, const Val& b) { Val z; sp::mont_mul(z, a, b); return z; }
     SR_D static void acc(Val& s, const Val& x) { Val t; sp::add(t, s, x); s = t; }

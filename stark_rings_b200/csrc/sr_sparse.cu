@@ -26,14 +26,19 @@ constexpr int SPMV_T = 128;
 template <class S>
 __global__ void __launch_bounds__(SPMV_T)
 sparse_matvec_kernel(const u64* __restrict__ row_ptr, const u64* __restrict__ col_idx, const u64* __restrict__ vals,
-                     const u64* __restrict__ v, size_t nrows, size_t ncols, u64* __restrict__ out, int* __restrict__ bad) {
+                     const u64* __restrict__ v, size_t nrows, size_t ncols, size_t nnz, u64* __restrict__ out,
+                     int* __restrict__ bad) {
     const size_t idx = (size_t)blockIdx.x * SPMV_T + threadIdx.x;
     if (idx >= nrows * S::SLOTS) return;
     const size_t row = idx / S::SLOTS;
     const int slot = (int)(idx - row * S::SLOTS);
     typename S::Accum acc;
     S::accum_zero(acc);
-    const u64 e0 = row_ptr[row], e1 = row_ptr[row + 1];
+    u64 e0 = row_ptr[row], e1 = row_ptr[row + 1];
+    if (e0 > e1 || e1 > nnz) {  // a malformed row_ptr must not turn into out-of-bounds reads
+        *bad = 2;
+        e1 = e0;
+    }
     for (u64 e = e0; e < e1; e++) {
         const u64 c = col_idx[e];
         if (c >= ncols) {  // the reference indexes v[*i] out of bounds and panics
@@ -53,7 +58,7 @@ template <class S>
 __global__ void __launch_bounds__(SPMV_T)
 sparse_matvec_warp_kernel(const u64* __restrict__ row_ptr, const u64* __restrict__ col_idx,
                           const u64* __restrict__ vals, const u64* __restrict__ v, size_t nrows, size_t ncols,
-                          u64* __restrict__ out, int* __restrict__ bad) {
+                          size_t nnz, u64* __restrict__ out, int* __restrict__ bad) {
     constexpr int SUBS = 32 / S::SLOTS;
     __shared__ typename S::Val red[SPMV_T];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -63,7 +68,11 @@ sparse_matvec_warp_kernel(const u64* __restrict__ row_ptr, const u64* __restrict
     typename S::Accum acc;
     S::accum_zero(acc);
     if (live) {
-        const u64 e0 = row_ptr[row], e1 = row_ptr[row + 1];
+        u64 e0 = row_ptr[row], e1 = row_ptr[row + 1];
+        if (e0 > e1 || e1 > nnz) {
+            *bad = 2;
+            e1 = e0;
+        }
         for (u64 e = e0 + sub; e < e1; e += SUBS) {
             const u64 c = col_idx[e];
             if (c >= ncols) {
@@ -106,6 +115,52 @@ matmat_kernel(const u64* const* __restrict__ a_rows, const u64* const* __restric
     S::store(out_rows[i] + j * S::ELEM_U64 + slot * S::SLOT_U64, S::accum_result(acc));
 }
 
+// Sparse x sparse product, numeric phase (SparseMatrix::checked_mul_mat, sparse_matrix.rs:219-275).  The symbolic phase
+// (which entries of row i of A meet which entries of column j of M: the reference's merge join over the stored index
+// order) depends on the indices only and is done by the caller (sr_sparse_matmat_symbolic); it yields, per candidate
+// output entry c, the pairs [pair_ptr[c], pair_ptr[c+1]) of (entry of A, entry of M).  Thread per (candidate, slot):
+// out[c] = sum of the pair products; nonzero[c] |= (some product is not the zero ELEMENT) -- the reference only adds
+// non-zero products, which changes nothing in the sum but decides whether the entry exists at all.
+template <class S>
+__global__ void __launch_bounds__(SPMV_T)
+sparse_pairs_kernel(const u64* __restrict__ a_vals, const u64* __restrict__ m_vals, const u64* __restrict__ pair_ptr,
+                    const u64* __restrict__ pair_a, const u64* __restrict__ pair_m, size_t ncand,
+                    u64* __restrict__ out, int* __restrict__ nonzero) {
+    const size_t idx = (size_t)blockIdx.x * SPMV_T + threadIdx.x;
+    if (idx >= ncand * S::SLOTS) return;
+    const size_t c = idx / S::SLOTS;
+    const int slot = (int)(idx - c * S::SLOTS);
+    typename S::Val sum = S::zero();
+    bool any = false;
+    for (u64 e = pair_ptr[c]; e < pair_ptr[c + 1]; e++) {
+        const typename S::Val a = S::load_cached(a_vals + pair_a[e] * S::ELEM_U64 + slot * S::SLOT_U64);
+        const typename S::Val x = S::load_cached(m_vals + pair_m[e] * S::ELEM_U64 + slot * S::SLOT_U64);
+        const typename S::Val prod = S::mul(a, x);
+        any = any || !S::is_zero(prod);
+        S::acc(sum, prod);
+    }
+    S::store(out + c * S::ELEM_U64 + slot * S::SLOT_U64, sum);
+    if (any) atomicOr(nonzero + c, 1);
+}
+template <class S>
+static cudaError_t sparse_pairs_t(const u64* a_vals, const u64* m_vals, const u64* pair_ptr, const u64* pair_a,
+                                  const u64* pair_m, size_t ncand, u64* out, int* nonzero, cudaStream_t st) {
+    if (ncand == 0) return cudaSuccess;
+    const size_t total = ncand * S::SLOTS;
+    sparse_pairs_kernel<S><<<(unsigned)((total + SPMV_T - 1) / SPMV_T), SPMV_T, 0, st>>>(a_vals, m_vals, pair_ptr, pair_a,
+                                                                                         pair_m, ncand, out, nonzero);
+    return cudaGetLastError();
+}
+cudaError_t sparse_pairs_launch(int ring, const u64* a_vals, const u64* m_vals, const u64* pair_ptr, const u64* pair_a,
+                                const u64* pair_m, size_t ncand, u64* out, int* nonzero, cudaStream_t st) {
+    switch (ring) {
+    case RING_GL: return sparse_pairs_t<GLSlot>(a_vals, m_vals, pair_ptr, pair_a, pair_m, ncand, out, nonzero, st);
+    case RING_BB: return sparse_pairs_t<BBSlot>(a_vals, m_vals, pair_ptr, pair_a, pair_m, ncand, out, nonzero, st);
+    case RING_SP: return sparse_pairs_t<SPSlot>(a_vals, m_vals, pair_ptr, pair_a, pair_m, ncand, out, nonzero, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 // a[e] <- a[e] * r for every element e of the batch; thread per (e, slot)
 template <class S>
 __global__ void __launch_bounds__(256)
@@ -124,11 +179,11 @@ static cudaError_t sparse_matvec_t(const u64* row_ptr, const u64* col_idx, const
     if (nrows == 0) return cudaSuccess;
     if (nnz / nrows >= 8) {
         const unsigned grid = (unsigned)((nrows + SPMV_T / 32 - 1) / (SPMV_T / 32));
-        sparse_matvec_warp_kernel<S><<<grid, SPMV_T, 0, st>>>(row_ptr, col_idx, vals, v, nrows, ncols, out, bad);
+        sparse_matvec_warp_kernel<S><<<grid, SPMV_T, 0, st>>>(row_ptr, col_idx, vals, v, nrows, ncols, nnz, out, bad);
     } else {
         const size_t total = nrows * S::SLOTS;
         sparse_matvec_kernel<S><<<(unsigned)((total + SPMV_T - 1) / SPMV_T), SPMV_T, 0, st>>>(row_ptr, col_idx, vals, v,
-                                                                                              nrows, ncols, out, bad);
+                                                                                              nrows, ncols, nnz, out, bad);
     }
     return cudaGetLastError();
 }

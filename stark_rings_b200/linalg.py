@@ -11,9 +11,10 @@ and of SparseMatrix for R = RqNTT (linear_algebra/src/sparse_matrix.rs), SURVEY.
   identity / from_dense / to_dense             sparse_matrix.rs:86-97,108-137
   checked_mul_vec / try_mul_vec / Mul<&[R]>    sparse_matrix.rs:201-217,278-286
   MulAssign<&R>                                sparse_matrix.rs:298-302
-The ring mat-vec is the hot path; the rest are the callers' neighbouring linear maps.  Padding, hconcat, rand,
-serialization and the sparse x sparse product (whose output structure depends on which products are zero,
-sparse_matrix.rs:219-275) stay with the caller.
+  checked_mul_mat / try_mul_mat / Mul<&SparseMatrix>  sparse_matrix.rs:219-275 -> SparseMatrix.checked_mul_mat / try_mul_mat
+  CanonicalSerialize / CanonicalDeserialize    matrix.rs:111-145, sparse_matrix.rs:157-200 -> serialize / deserialize
+The ring mat-vec is the hot path; the rest are the callers' neighbouring linear maps.  Padding, hconcat and rand stay
+with the caller.
 """
 from __future__ import annotations
 
@@ -136,6 +137,48 @@ class Matrix:
             _scale(row, r, self.ctx)
         return self
 
+    # -- CanonicalSerialize / CanonicalDeserialize (matrix.rs:111-145): self.vals: Vec<Vec<R>>, i.e. ark-serialize's
+    # u64 little-endian length prefix of the outer Vec, then per row its own u64 length and the elements back to back
+    # (each element = D field elements, standard-form little-endian, no prefix: coeff_form.rs:154-189).  The element
+    # bytes are produced on the device for device-resident rows (sr_serialize_batch); the framing is host work.
+    def serialize(self) -> np.ndarray:
+        parts = [np.array([self.nrows], dtype="<u8").view(np.uint8)]
+        for r in self.vals:
+            parts.append(np.array([len(r)], dtype="<u8").view(np.uint8))
+            b = r.serialize()
+            parts.append(b if isinstance(b, np.ndarray) else b.cpu().numpy())
+        return np.concatenate(parts)
+
+    @classmethod
+    def deserialize(cls, config, data: np.ndarray, device=None, ctx=None) -> "Matrix":
+        """matrix.rs:131-145: nrows = vals.len(), ncols = the first row's length.  Raises LengthPanic on a truncated
+        buffer and StarkRingsError on a non-canonical field element (SerializationError::InvalidData)."""
+        from .errors import LengthPanic
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        per = int(L.lib.sr_serialized_bytes(config.ring_id, 1))
+        pos = 0
+
+        def u64():
+            nonlocal pos
+            if pos + 8 > data.size:
+                raise LengthPanic("serialized matrix is truncated")
+            v = int(data[pos:pos + 8].view("<u8")[0])
+            pos += 8
+            return v
+        rows = []
+        for _ in range(u64()):
+            n = u64()
+            if pos + n * per > data.size:
+                raise LengthPanic("serialized matrix is truncated")
+            chunk = data[pos:pos + n * per]
+            pos += n * per
+            src = torch.from_numpy(chunk.copy()).to(device) if device is not None else chunk.copy()
+            rows.append(RqNTT.deserialize(config, src, ctx))
+        m = cls.__new__(cls)
+        m.vals, m.nrows, m.ctx, m.config = rows, len(rows), ctx, config
+        m.ncols = len(rows[0]) if rows else 0
+        return m
+
     def partial_mul_vec(self, v: RqNTT) -> RqNTT:
         """One rank's share of a column-sharded commitment (sr_matvec_partial)."""
         out = self._call(L.lib.sr_matvec_partial, v)
@@ -238,6 +281,122 @@ class SparseMatrix:
         return self.try_mul_vec(v)
 
     __mul__ = __matmul__
+
+    def checked_mul_mat(self, m: "SparseMatrix"):
+        """sparse_matrix.rs:219-275: None when self.ncols != m.nrows.  The structure pass (columns of m in row order,
+        merge join of the index lists in stored order) runs on the host exactly as in the reference
+        (sr_sparse_matmat_symbolic); the products and sums run on the device (sr_sparse_matmat_values); an output entry
+        exists iff one of its products is not the zero element, and the rows come out ordered by column."""
+        if self.ncols != m.nrows:
+            return None
+        cfg = self.config
+        if m.config is not cfg:
+            raise TypeError("matrices are over different rings")
+        host = lambda a: a if isinstance(a, np.ndarray) else a.cpu().numpy().view(np.uint64)
+        arp, aci = np.ascontiguousarray(host(self.row_ptr)), np.ascontiguousarray(host(self.col_idx))
+        mrp, mci = np.ascontiguousarray(host(m.row_ptr)), np.ascontiguousarray(host(m.col_idx))
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data) if a.size else None
+        ncand, npairs = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        sym = lambda *outs: L.lib.sr_sparse_matmat_symbolic(self.nrows, vp(arp), vp(aci), m.nrows, m.ncols, vp(mrp), vp(mci),
+                                                            ctypes.byref(ncand), ctypes.byref(npairs), *outs)
+        if sym(None, None, None, None, None) != L.SR_OK:
+            raise ValueError("malformed CSR arrays (the reference panics on an out-of-range column of m)")
+        nc, npr = ncand.value, npairs.value
+        cand_row, cand_col = np.empty(nc, dtype=np.uint64), np.empty(nc, dtype=np.uint64)
+        pair_ptr = np.zeros(nc + 1, dtype=np.uint64)
+        pair_a, pair_m = np.empty(max(npr, 1), dtype=np.uint64), np.empty(max(npr, 1), dtype=np.uint64)
+        if nc:
+            sym(vp(cand_row), vp(cand_col), vp(pair_ptr), vp(pair_a), vp(pair_m))
+        pa, _, loc, dev = _ptr_loc(self.vals.data) if len(self.vals) else (None, 0, L.SR_HOST, None)
+        pm, _, locm, _ = _ptr_loc(m.vals.data) if len(m.vals) else (None, 0, loc, None)
+        if len(self.vals) and len(m.vals) and locm != loc:
+            raise ValueError("both matrices must live in the same place")
+        on_dev = loc == L.SR_DEVICE
+        like = self.vals.data
+        out_vals = (torch.empty(max(nc, 1) * cfg.limbs, dtype=like.dtype, device=like.device) if on_dev
+                    else np.empty(max(nc, 1) * cfg.limbs, dtype=np.uint64))
+        nz = np.zeros(max(nc, 1), dtype=np.int32)
+        c = self.ctx or self.vals.ctx or default_context(0 if dev is None else dev)
+        if nc:
+            if on_dev:
+                c.use_torch_stream()
+            c.check(L.lib.sr_sparse_matmat_values(c.h, cfg.ring_id, pa, pm, nc, vp(pair_ptr), vp(pair_a), vp(pair_m),
+                                                  _ptr_loc(out_vals)[0], ctypes.c_void_p(nz.ctypes.data), loc),
+                    "sr_sparse_matmat_values")
+        keep = np.nonzero(nz[:nc])[0]
+        row_ptr = np.zeros(self.nrows + 1, dtype=np.uint64)
+        np.add.at(row_ptr, cand_row[keep].astype(np.int64) + 1, 1)
+        row_ptr = np.cumsum(row_ptr).astype(np.uint64)
+        col_idx = cand_col[keep]
+        w = cfg.limbs
+        if on_dev:
+            idx = torch.from_numpy(keep.astype(np.int64)).to(like.device)
+            vals = out_vals.view(-1, w)[: max(nc, 1)].index_select(0, idx).reshape(-1).contiguous()
+            to = lambda a: torch.from_numpy(a.view(np.int64)).to(like.device)
+            return SparseMatrix(self.nrows, m.ncols, to(row_ptr), to(col_idx), RqNTT(cfg, vals, c), c)
+        vals = out_vals.reshape(-1, w)[keep].reshape(-1).copy()
+        return SparseMatrix(self.nrows, m.ncols, row_ptr, col_idx, RqNTT(cfg, vals, c), c)
+
+    def try_mul_mat(self, m: "SparseMatrix") -> "SparseMatrix":
+        """sparse_matrix.rs:271-275: Err(AlgebraError::DifferentLengths(self.ncols, m.nrows))."""
+        out = self.checked_mul_mat(m)
+        if out is None:
+            raise DifferentLengths(self.ncols, m.nrows)
+        return out
+
+    # -- CanonicalSerialize / CanonicalDeserialize (sparse_matrix.rs:157-200): nrows and ncols as u64, then
+    # coeffs: Vec<Vec<(R, usize)>>: u64 row count, per row its u64 length and the (element bytes, u64 column) tuples.
+    def serialize(self) -> np.ndarray:
+        host = lambda a: a if isinstance(a, np.ndarray) else a.cpu().numpy().view(np.uint64)
+        rp, ci = host(self.row_ptr), host(self.col_idx)
+        b = self.vals.serialize() if len(self.vals) else np.empty(0, dtype=np.uint8)
+        b = b if isinstance(b, np.ndarray) else b.cpu().numpy()
+        per = int(L.lib.sr_serialized_bytes(self.config.ring_id, 1))
+        nnz = len(ci)
+        rec = np.empty((nnz, per + 8), dtype=np.uint8)
+        rec[:, :per] = b.reshape(nnz, per)
+        rec[:, per:] = np.ascontiguousarray(ci, dtype="<u8").view(np.uint8).reshape(nnz, 8)
+        parts = [np.array([self.nrows, self.ncols, self.nrows], dtype="<u8").view(np.uint8)]
+        for i in range(self.nrows):
+            e0, e1 = int(rp[i]), int(rp[i + 1])
+            parts.append(np.array([e1 - e0], dtype="<u8").view(np.uint8))
+            parts.append(rec[e0:e1].reshape(-1))
+        return np.concatenate(parts)
+
+    @classmethod
+    def deserialize(cls, config, data: np.ndarray, device=None, ctx=None) -> "SparseMatrix":
+        from .errors import LengthPanic
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        per = int(L.lib.sr_serialized_bytes(config.ring_id, 1))
+        pos = 0
+
+        def u64():
+            nonlocal pos
+            if pos + 8 > data.size:
+                raise LengthPanic("serialized sparse matrix is truncated")
+            v = int(data[pos:pos + 8].view("<u8")[0])
+            pos += 8
+            return v
+        nrows, ncols, outer = u64(), u64(), u64()
+        row_ptr = np.zeros(outer + 1, dtype=np.uint64)
+        elem_bytes, cols = [], []
+        for i in range(outer):
+            n = u64()
+            if pos + n * (per + 8) > data.size:
+                raise LengthPanic("serialized sparse matrix is truncated")
+            rec = data[pos:pos + n * (per + 8)].reshape(n, per + 8)
+            pos += n * (per + 8)
+            elem_bytes.append(rec[:, :per].reshape(-1))
+            cols.append(np.ascontiguousarray(rec[:, per:]).view("<u8").reshape(-1))
+            row_ptr[i + 1] = row_ptr[i] + n
+        eb = np.concatenate(elem_bytes) if elem_bytes else np.empty(0, dtype=np.uint8)
+        col_idx = (np.concatenate(cols) if cols else np.empty(0, dtype=np.uint64)).astype(np.uint64)
+        src = torch.from_numpy(eb.copy()).to(device) if device is not None else eb.copy()
+        vals = RqNTT.deserialize(config, src, ctx)
+        if device is not None:
+            to = lambda a: torch.from_numpy(a.view(np.int64)).to(device)
+            return cls(nrows, ncols, to(row_ptr), to(col_idx), vals, ctx)
+        return cls(nrows, ncols, row_ptr, col_idx, vals, ctx)
 
     def __imul__(self, r: RqNTT) -> "SparseMatrix":
         """sparse_matrix.rs:298-302: every stored entry *= r."""

@@ -183,6 +183,38 @@ class RingConfig:
         c.check(fn(c.h, pa, pb, na, loc), "ntt_mul_batch")
         return a_inout
 
+    def _addsub(self, which, a_inout, b, ctx=None):
+        pa, na, loc, dev = _ptr_loc(a_inout)
+        c = self._ctx(dev, ctx)
+        if which == "neg":
+            c.check(L.lib.sr_neg_batch(c.h, self.ring_id, pa, na, loc), "sr_neg_batch")
+            return a_inout
+        pb, nb, locb, _ = _ptr_loc(b)
+        if na != nb or loc != locb:
+            raise LengthPanic("%s: operands differ in length or location" % which)
+        fn = L.lib.sr_add_batch if which == "add" else L.lib.sr_sub_batch
+        c.check(fn(c.h, self.ring_id, pa, pb, na, loc), "sr_%s_batch" % which)
+        return a_inout
+
+    def add_batch(self, a_inout, b, ctx=None):
+        """a[i] += b[i] (ntt_form.rs:588-601 / coeff_form.rs Add: field element by field element in either form)."""
+        return self._addsub("add", a_inout, b, ctx)
+
+    def sub_batch(self, a_inout, b, ctx=None):
+        return self._addsub("sub", a_inout, b, ctx)
+
+    def neg_batch(self, a_inout, ctx=None):
+        return self._addsub("neg", a_inout, None, ctx)
+
+    def sum_batch(self, buf, ctx=None):
+        """Sum of a slice of elements (ntt_form.rs:640-654: fold from ZERO with Add) -> one element."""
+        p, n, loc, dev = _ptr_loc(buf)
+        out = (np.empty(self.limbs, dtype=np.uint64) if isinstance(buf, np.ndarray)
+               else torch.empty(self.limbs, dtype=buf.dtype, device=buf.device))
+        c = self._ctx(dev, ctx)
+        c.check(L.lib.sr_sum_batch(c.h, self.ring_id, p, n, _ptr_loc(out)[0], loc), "sr_sum_batch")
+        return out
+
     def reduce_batch(self, polys, coeffs_per_poly, ctx=None):
         """CyclotomicConfig::reduce_in_place on a batch (ring_config.rs:23): polynomials of coeffs_per_poly field
         elements (D <= coeffs_per_poly <= 2D) -> coefficient-form ring elements (new buffer)."""
@@ -270,9 +302,42 @@ class _RqBase:
     def __len__(self):
         return _ptr_loc(self.data)[1] // self.config.limbs
 
-    @classmethod
-    def dimension(cls):  # PolyRing::dimension is per type in the reference; here per config
-        raise NotImplementedError
+    def dimension(self) -> int:
+        """PolyRing::dimension (coeff_form.rs:539-566, ntt_form.rs:672-697): the const generic D of the type, i.e. the
+        number of base-field coefficients per element; here a property of the element's ring configuration."""
+        return self.config.D
+
+    # -- Add / Sub / Neg / Sum (ntt_form.rs:588-626, 640-654 and the same operators of coeff_form.rs) -----------------
+    def __add__(self, rhs):
+        self._same(rhs)
+        out = self.clone()
+        self.config.add_batch(out.data, rhs.data, self.ctx)
+        return out
+
+    def __iadd__(self, rhs):
+        self._same(rhs)
+        self.config.add_batch(self.data, rhs.data, self.ctx)
+        return self
+
+    def __sub__(self, rhs):
+        self._same(rhs)
+        out = self.clone()
+        self.config.sub_batch(out.data, rhs.data, self.ctx)
+        return out
+
+    def __isub__(self, rhs):
+        self._same(rhs)
+        self.config.sub_batch(self.data, rhs.data, self.ctx)
+        return self
+
+    def __neg__(self):
+        out = self.clone()
+        self.config.neg_batch(out.data, self.ctx)
+        return out
+
+    def sum(self):
+        """Sum over the batch -> a batch of one element."""
+        return type(self)(self.config, self.config.sum_batch(self.data, self.ctx), self.ctx)
 
     def clone(self):
         d = self.data.copy() if isinstance(self.data, np.ndarray) else self.data.clone()

@@ -140,3 +140,20 @@ def test_gadget_decompose_properties(name, b):
             O.gadget_decompose(M, elems, b, 1)
         with pytest.raises(IndexError):
             C.gadget_decompose(name, flat(M, elems), b, 1)
+
+
+@pytest.mark.parametrize("name", ["goldilocks", "babybear", "stark_prime"])
+def test_addsub_sum_match_the_python_oracle(name):
+    """Element-wise Add / Sub / Neg and Sum (ntt_form.rs:588-626, 640-654): the C oracle against big-int arithmetic."""
+    from oracle import ref_py as O
+    from tests.util import rand_raw
+    M = O.MODELS[name]
+    n = 7
+    a, b = rand_raw(name, n, 1), rand_raw(name, n, 2)
+    va, vb = O.from_raw(M, a.tolist()), O.from_raw(M, b.tolist())
+    assert O.from_raw(M, C.addsub(name, "add", a, b).tolist()) == [(x + y) % M.p for x, y in zip(va, vb)]
+    assert O.from_raw(M, C.addsub(name, "sub", a, b).tolist()) == [(x - y) % M.p for x, y in zip(va, vb)]
+    assert O.from_raw(M, C.addsub(name, "neg", a).tolist()) == [(-x) % M.p for x in va]
+    got = O.from_raw(M, C.ring_sum(name, a).tolist())
+    assert got == [sum(va[e * M.D + i] for e in range(n)) % M.p for i in range(M.D)]
+    assert not C.ring_sum(name, a[:0]).any()

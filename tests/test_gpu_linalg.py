@@ -179,3 +179,166 @@ def test_serialize_deserialize(S, name, n):
     with pytest.raises(S.LengthPanic):
         S.RqPoly.deserialize(cfg, want[:-1].copy())
     assert S.RqPoly.deserialize(cfg, np.empty(0, dtype=np.uint8)).data.size == 0
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("n", [1, 3, 1000, 70001])
+def test_add_sub_neg_sum(S, name, n):
+    """Stand-alone element-wise Add / Sub / Neg and Sum on resident batches (ntt_form.rs:588-626, 640-654;
+    VERDICT r01 missing #3), device and host buffers, operators of both host mirrors' forms."""
+    cfg = S.CONFIGS[name]
+    a, b = rand_raw(name, n, 11 + n), rand_raw(name, n, 12 + n)
+    want_add, want_sub, want_neg = C.addsub(name, "add", a, b), C.addsub(name, "sub", a, b), C.addsub(name, "neg", a)
+    want_sum = C.ring_sum(name, a)
+    for Form in (S.RqNTT, S.RqPoly):
+        x, y = Form(cfg, dev(a)), Form(cfg, dev(b))
+        assert np.array_equal(host((x + y).data), want_add)
+        assert np.array_equal(host((x - y).data), want_sub)
+        assert np.array_equal(host((-x).data), want_neg)
+        assert np.array_equal(host(x.data), a)  # operands untouched
+        assert np.array_equal(host(x.sum().data), want_sum)
+        x += y
+        assert np.array_equal(host(x.data), want_add)
+        x -= y
+        assert np.array_equal(host(x.data), a)
+        assert x.dimension() == cfg.D
+    # host buffers through the same entry points
+    xh, yh = S.RqNTT(cfg, a.copy()), S.RqNTT(cfg, b.copy())
+    assert np.array_equal((xh + yh).data, want_add)
+    assert np.array_equal((xh - yh).data, want_sub)
+    assert np.array_equal((-xh).data, want_neg)
+    assert np.array_equal(xh.sum().data, want_sum)
+    # a + (-a) = 0, Sum of nothing = ZERO
+    z = S.RqNTT(cfg, dev(a)) + (-S.RqNTT(cfg, dev(a)))
+    assert not host(z.data).any()
+    assert not cfg.sum_batch(np.empty(0, dtype=np.uint64)).any()
+    with pytest.raises(S.LengthPanic):
+        cfg.add_batch(dev(a), dev(b)[: len(b) - 1] if n > 1 else dev(np.zeros(1, dtype=np.uint64)))
+
+
+def _sparse_matmat_oracle(name, a_coeffs, m_coeffs, m_ncols):
+    """SparseMatrix::checked_mul_mat restated statement by statement (sparse_matrix.rs:219-275) on lists of
+    (element limbs, index) with the C oracle's ring arithmetic."""
+    m_cols = [[] for _ in range(m_ncols)]
+    for row_idx, row in enumerate(m_coeffs):
+        for val, col_idx in row:
+            m_cols[col_idx].append((val, row_idx))
+    out = []
+    for row in a_coeffs:
+        res_row = []
+        for j, col in enumerate(m_cols):
+            s, ri, ci = None, 0, 0
+            while ri < len(row) and ci < len(col):
+                (r_val, r_idx), (c_val, c_idx) = row[ri], col[ci]
+                if r_idx < c_idx:
+                    ri += 1
+                elif r_idx > c_idx:
+                    ci += 1
+                else:
+                    prod = C.ntt_mul(name, r_val.copy(), c_val.copy())
+                    if prod.any():
+                        s = prod if s is None else C.addsub(name, "add", s, prod)
+                    ri += 1
+                    ci += 1
+            if s is not None:
+                res_row.append((s, j))
+        out.append(res_row)
+    return out
+
+
+def _coeffs_equal(a, b):
+    return len(a) == len(b) and all(
+        len(ra) == len(rb) and all(ja == jb and np.array_equal(va, vb) for (va, ja), (vb, jb) in zip(ra, rb))
+        for ra, rb in zip(a, b))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_sparse_matmat_reference_kat(S, name):
+    """sparse_matrix.rs:375-388: sample_sparse * [[1, 2], [3, 4], [5, 6]] = [[6, 8], [0, 0], [28, 36]] (the zero row has
+    no entries); a 2-row right factor is Err(DifferentLengths)."""
+    cfg, M = S.CONFIGS[name], O.MODELS[name]
+    const = lambda c: np.array(O.to_raw(M, M.crt([c] + [0] * (M.D - 1))), dtype=np.uint64)
+    a_coeffs = [[(const(2), 1)], [], [(const(1), 0), (const(4), 1), (const(3), 2)]]
+    m_coeffs = [[(const(1), 0), (const(2), 1)], [(const(3), 0), (const(4), 1)], [(const(5), 0), (const(6), 1)]]
+    want = [[(const(6), 0), (const(8), 1)], [], [(const(28), 0), (const(36), 1)]]
+    for device in (None, "cuda"):
+        A = S.SparseMatrix.from_coeffs(cfg, 3, 3, a_coeffs, device=device)
+        Mx = S.SparseMatrix.from_coeffs(cfg, 3, 2, m_coeffs, device=device)
+        P = A.try_mul_mat(Mx)
+        assert (P.nrows, P.ncols) == (3, 2)
+        assert _coeffs_equal(P.to_coeffs(), want)
+        M3 = S.SparseMatrix.from_coeffs(cfg, 2, 2, m_coeffs[:2], device=device)
+        assert A.checked_mul_mat(M3) is None
+        with pytest.raises(S.DifferentLengths) as ei:
+            A.try_mul_mat(M3)
+        assert ei.value.lengths == (3, 2)
+
+
+@pytest.mark.parametrize("name", ALL)
+@pytest.mark.parametrize("nrows,inner,ncols,density", [(5, 7, 4, 0.5), (40, 30, 25, 0.15), (3, 200, 2, 0.9)])
+def test_sparse_matmat_random(S, name, nrows, inner, ncols, density):
+    """Random sorted CSR factors, including explicit zero ELEMENTS (a stored zero makes a zero product, which the
+    reference does not count: an output entry made only of such products must not exist)."""
+    cfg = S.CONFIGS[name]
+    w = WORDS[name]
+    rng = np.random.default_rng(nrows * 1000 + inner)
+
+    def rand_sparse(nr, nc, seed):
+        coeffs = []
+        pool = rand_raw(name, nr * nc + 2, seed, edge=False).reshape(-1, w)
+        k = 0
+        for i in range(nr):
+            cols = [j for j in range(nc) if rng.random() < density]
+            row = []
+            for j in cols:
+                val = np.zeros(w, dtype=np.uint64) if rng.random() < 0.15 else pool[k].copy()
+                k += 1
+                row.append((val, j))
+            coeffs.append(row)
+        return coeffs
+    a_coeffs, m_coeffs = rand_sparse(nrows, inner, 5), rand_sparse(inner, ncols, 6)
+    want = _sparse_matmat_oracle(name, a_coeffs, m_coeffs, ncols)
+    for device in (None, "cuda"):
+        A = S.SparseMatrix.from_coeffs(cfg, nrows, inner, a_coeffs, device=device)
+        Mx = S.SparseMatrix.from_coeffs(cfg, inner, ncols, m_coeffs, device=device)
+        assert _coeffs_equal(A.try_mul_mat(Mx).to_coeffs(), want)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_matrix_container_serialization(S, name):
+    """Matrix / SparseMatrix CanonicalSerialize (matrix.rs:111-145, sparse_matrix.rs:157-200): ark-serialize's Vec
+    framing (u64 little-endian lengths) around the element bytes; byte-for-byte against the framing built from the
+    oracle's element serialization, and round trips (host and device)."""
+    cfg = S.CONFIGS[name]
+    w = WORDS[name]
+    le = lambda x: np.array([x], dtype="<u8").view(np.uint8)
+    rows = [rand_raw(name, 5, 60 + i) for i in range(3)]
+    want = np.concatenate([le(3)] + [np.concatenate([le(5), C.serialize(name, r)]) for r in rows])
+    for device in (None, "cuda"):
+        A = S.Matrix([S.RqNTT(cfg, dev(r) if device else r.copy()) for r in rows])
+        got = A.serialize()
+        assert np.array_equal(got, want)
+        B = S.Matrix.deserialize(cfg, got, device=device)
+        assert (B.nrows, B.ncols) == (3, 5)
+        for r, br in zip(rows, B.vals):
+            assert np.array_equal(host(br.data) if device else br.data, r)
+    with pytest.raises(S.LengthPanic):
+        S.Matrix.deserialize(cfg, want[:-3])
+    assert S.Matrix.deserialize(cfg, le(0)).nrows == 0
+    # sparse: nrows, ncols, then Vec<Vec<(R, usize)>>
+    elems = rand_raw(name, 4, 77).reshape(4, w)
+    coeffs = [[(elems[0], 1)], [], [(elems[1], 0), (elems[2], 2), (elems[3], 5)]]
+    ser1 = lambda e: C.serialize(name, np.ascontiguousarray(e))
+    want = np.concatenate([le(3), le(6), le(3),
+                           le(1), ser1(elems[0]), le(1),
+                           le(0),
+                           le(3), ser1(elems[1]), le(0), ser1(elems[2]), le(2), ser1(elems[3]), le(5)])
+    for device in (None, "cuda"):
+        A = S.SparseMatrix.from_coeffs(cfg, 3, 6, coeffs, device=device)
+        got = A.serialize()
+        assert np.array_equal(got, want)
+        B = S.SparseMatrix.deserialize(cfg, got, device=device)
+        assert (B.nrows, B.ncols) == (3, 6)
+        assert _coeffs_equal(B.to_coeffs(), coeffs)
+    with pytest.raises(S.LengthPanic):
+        S.SparseMatrix.deserialize(cfg, want[:-1])
