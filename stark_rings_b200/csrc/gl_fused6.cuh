@@ -22,49 +22,19 @@
 namespace sr {
 namespace gl {
 
-// lo + top * 2^64 (top < 2^32) -> weak residue
-SR_HD u64 red96(u64 lo, u32 top) {
-#if defined(__CUDA_ARCH__)
-    return add_eps_mul(lo, top);
-#else
-    return reduce128(lo, top);
-#endif
+// quarter q holds f mod X^6 - rho_q with rho_q the squares of the stage-3 roots 1, 7, 5, 11 (ntt.rs:196-225):
+// rho = r^2, r^14, r^10, r^22 = 2^80, -2^80, 2^16, -2^16.  The quarter index is uniform across the warp (it is the loop
+// trip), so the multiplication by rho_q is a uniform four-way branch over COMPILE-TIME shift-reductions (about a
+// third of the instructions of a shift by a runtime exponent: no funnel shifts by a register, no word-rotation
+// branches, the negation folded into the last subtraction).
+template <int Q>
+SR_HD u64 mul_rho(u64 y) {
+    constexpr int E[4] = {root_exp(2), root_exp(14), root_exp(10), root_exp(22)};
+    return mul_pow2<E[Q]>(y);
 }
-
-// x * 2^E, E in [0, 192) a RUNTIME exponent that is uniform across the warp (it depends on the loop trip only);
-// weak in, weak out.  E = 96 q + 32 j + s: the shift by s is a funnel shift, the word rotation j a uniform branch,
-// q a final negation (2^96 = -1).
-SR_HD u64 mul_pow2_rt(u64 x, int E) {
-    const int q = E >= 96, KK = q ? E - 96 : E, j = KK >> 5, s = KK & 31;
-    const u32 xl = (u32)x, xh = (u32)(x >> 32);
 #if defined(__CUDA_ARCH__)
-    const u32 v0 = xl << s, v1 = __funnelshift_l(xl, xh, s), v2 = __funnelshift_l(xh, 0u, s);
-#else
-    const u32 v0 = xl << s, v1 = s ? (xh << s) | (xl >> (32 - s)) : xh, v2 = s ? xh >> (32 - s) : 0u;
-#endif
-    u64 r;
-    if (j == 0) {
-        r = red96((u64)v0 | ((u64)v1 << 32), v2);              // v0 + v1 2^32 + v2 2^64
-    } else if (j == 1) {
-        r = sub(red96((u64)v0 << 32, v1), (u64)v2);            // v0 2^32 + v1 2^64 - v2
-    } else {
-        r = sub(red96(0, v0), (u64)v1 | ((u64)v2 << 32));      // v0 2^64 - v1 - v2 2^32 (v2 < 2^31: canonical)
-    }
-    return q ? neg(r) : r;
-}
-
-// quarter q holds f mod X^6 - 2^e_q: the squares of the stage-3 roots 1, 7, 5, 11 (ntt.rs:196-225)
-#define SR_GL_SEXTIC_EXPS \
-    {(unsigned char)root_exp(2), (unsigned char)root_exp(14), (unsigned char)root_exp(10), (unsigned char)root_exp(22)}
-#if defined(__CUDACC__)
-static __constant__ unsigned char c_sextic_exps[4] = SR_GL_SEXTIC_EXPS;
-#endif
-#if defined(__CUDA_ARCH__)
-#define SR_GL_TAB(name) c_##name
 #define SR_GL_ROLL _Pragma("unroll 1")
 #else
-static const unsigned char h_sextic_exps[4] = SR_GL_SEXTIC_EXPS;
-#define SR_GL_TAB(name) h_##name
 #define SR_GL_ROLL
 #endif
 
@@ -93,13 +63,25 @@ SR_HD void row_store(u64* row, const u64 (&c)[D]) {
     for (int i = 0; i < D; i += 2) st2(row + i, c[i], c[i + 1]);
 }
 
-// z <- x * y modulo X^6 - 2^E (E a warp-uniform runtime exponent); output CANONICAL.
+// z <- x * y modulo X^6 - rho_q (q warp-uniform); output CANONICAL.
 // y_1..y_5 are pre-multiplied by rho (five shift-reductions), after which output k is one lazy sum of six products:
 // sum_{i <= k} x_i y_{k-i} + sum_{i > k} x_i (rho y_{k+6-i}).
-SR_HD void sextic_mul(u64 (&z)[6], const u64 (&x)[6], const u64 (&y)[6], int E) {
+SR_HD void sextic_mul(u64 (&z)[6], const u64 (&x)[6], const u64 (&y)[6], int q) {
     u64 ry[6];
+    ry[0] = 0;
+    if (q == 0) {
 #pragma unroll
-    for (int i = 1; i < 6; i++) ry[i] = mul_pow2_rt(y[i], E);
+        for (int i = 1; i < 6; i++) ry[i] = mul_rho<0>(y[i]);
+    } else if (q == 1) {
+#pragma unroll
+        for (int i = 1; i < 6; i++) ry[i] = mul_rho<1>(y[i]);
+    } else if (q == 2) {
+#pragma unroll
+        for (int i = 1; i < 6; i++) ry[i] = mul_rho<2>(y[i]);
+    } else {
+#pragma unroll
+        for (int i = 1; i < 6; i++) ry[i] = mul_rho<3>(y[i]);
+    }
 #pragma unroll
     for (int k = 0; k < 6; k++) {
 #if defined(__CUDA_ARCH__)
@@ -127,7 +109,7 @@ SR_HD void sextic_products(u64* rowA, const u64* rowB) {
             ld2(rowA + 6 * q + i, x[i], x[i + 1]);
             ld2(rowB + 6 * q + i, y[i], y[i + 1]);
         }
-        sextic_mul(z, x, y, SR_GL_TAB(sextic_exps)[q]);
+        sextic_mul(z, x, y, q);
 #pragma unroll
         for (int i = 0; i < 6; i += 2) st2(rowA + 6 * q + i, z[i], z[i + 1]);
     }

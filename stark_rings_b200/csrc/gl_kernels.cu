@@ -8,25 +8,12 @@ namespace sr {
 // four 4-warp CTAs left the SM waiting on global loads (ncu: long_scoreboard 27% of the stall samples in ntt_mul).
 // n = 2^22, T = 128 x 4 -> 64 x 8 -> 32 x 16: ring_mul 0.324 -> 0.334 -> 0.340, ntt_mul 0.648 -> 0.692 -> 0.732,
 // crt 0.763 -> 0.805 -> 0.824, icrt 0.512 -> 0.520 -> 0.519 of the HBM roofline.
-#ifndef SR_GL_T
-#define SR_GL_T 32
-#endif
-#ifndef SR_GL_RM_T   // fused ring mul: threads per CTA / resident CTAs per SM
-#define SR_GL_RM_T 32
-#endif
-#ifndef SR_GL_RM_MINB
-#define SR_GL_RM_MINB 16
-#endif
-#ifndef SR_GL_MINB
-#define SR_GL_MINB 16
-#endif
-
 cudaError_t gl_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms) {
     switch (op) {
-    case OP_CRT: return launch_batch_op<GLPolicy, OP_CRT, SR_GL_T, SR_GL_MINB>(a, b, out, n, st, sms);
-    case OP_ICRT: return launch_batch_op<GLPolicy, OP_ICRT, SR_GL_T, SR_GL_MINB>(a, b, out, n, st, sms);
-    case OP_NTT_MUL: return launch_batch_op<GLPolicy, OP_NTT_MUL, SR_GL_T, SR_GL_MINB>(a, b, out, n, st, sms);
-    case OP_RING_MUL: return launch_batch_op<GLPolicy, OP_RING_MUL, SR_GL_RM_T, SR_GL_RM_MINB>(a, b, out, n, st, sms);
+    case OP_CRT: return launch_batch_op<GLPolicy, OP_CRT, 32, 16>(a, b, out, n, st, sms);
+    case OP_ICRT: return launch_batch_op<GLPolicy, OP_ICRT, 32, 16>(a, b, out, n, st, sms);
+    case OP_NTT_MUL: return launch_batch_op<GLPolicy, OP_NTT_MUL, 32, 16>(a, b, out, n, st, sms);
+    case OP_RING_MUL: return launch_batch_op<GLPolicy, OP_RING_MUL, 32, 16>(a, b, out, n, st, sms);
     }
     return cudaErrorInvalidValue;
 }

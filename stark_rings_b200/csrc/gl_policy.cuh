@@ -47,36 +47,9 @@ struct GLPolicy {
         gl::ntt_mul_rolled(reinterpret_cast<u64*>(rowA), reinterpret_cast<const u64*>(rowB));
     }
     SR_D static void op_ring_mul(u32* rowA, const u32* rowB) {
-#if !defined(SR_GL_RM_UNROLLED) && !defined(SR_GL_RM_LOOP)  // default: degree-6 formulation (gl_fused6.cuh)
         int trips = 2;
         asm volatile("" : "+r"(trips));  // opaque trip count: one copy of the forward transform
         gl::ring_mul_fused6(reinterpret_cast<u64*>(rowA), reinterpret_cast<u64*>(const_cast<u32*>(rowB)), trips);
-#elif defined(SR_GL_RM_LOOP)
-        // One copy of the forward transform for both operands (a real 2-trip loop): the instruction footprint of the
-        // kernel drops by a sixth and the second trip re-runs code that is still in the instruction cache.  crt(a)
-        // is parked in the thread's shared-memory row and read back slot by slot.
-        u64 b[24];
-        int trips = 2;
-        asm volatile("" : "+r"(trips));  // opaque trip count: keeps ptxas from peeling the loop back into two copies
-        const ptrdiff_t delta = rowB - rowA;
-#pragma unroll 1
-        for (int k = 0; k < trips; k++) {
-            u32* row = rowA + k * delta;
-            load(b, row);
-            gl::crt_stages(b);
-            store(row, b);
-        }
-        gl::fused_mul_icrt(b, reinterpret_cast<const u64*>(rowA));
-        store(rowA, b);
-#else
-        u64 a[24], b[24];
-        load(a, rowA);
-        gl::crt_stages(a);
-        load(b, rowB);
-        gl::crt_stages(b);
-        gl::fused_mul_icrt(b, a);
-        store(rowA, b);
-#endif
     }
 };
 

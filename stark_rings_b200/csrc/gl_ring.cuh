@@ -328,37 +328,43 @@ SR_D void acc_mad(Acc& A, u64 a, u64 b) {
         : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3)
         : "r"(al), "r"(ah), "r"(bl), "r"(bh));
 }
-// canonical residue of the accumulated value; valid while the true sum is < 2^160 (up to 2^32 products)
+// canonical residue of the accumulated value; valid while the true sum is < 2^160 (up to 2^32 products).
+// With T = 2^32 (T^2 = T - 1, T^3 = -1, T^4 = -T mod p) the value e0 + (e1+o1) T + (e2+o2) T^2 + (e3+o3) T^3 + e4 T^4
+// is  X + Y T  with  X = e0 - (e2+o2) - (e3+o3)  in (-2^34, 2^32)  and  Y = (e1+o1) + (e2+o2) - e4  in (-2^32, 2^34):
+// two signed 64-bit sums (no carry chain through the limbs, no E/O merge), then V = X + Y T + 16 p > 0 as a 128-bit
+// integer whose small high word is folded with 2^64 = 2^32 - 1.  About half the instructions of the limb-by-limb
+// merge followed by reduce128 / sub / canon.
+SR_D u64 fold_xy(u64 X, u64 Y) {  // X, Y two's-complement 64-bit, |X|, |Y| < 2^35
+    // V = X + (Y << 32) + 16 p > 0 (|V| < 2^67 + 2^35, 16 p = 2^68 - 2^36 + 16): low 64 bits and the small high word
+    const u64 ylo = Y << 32;                       // (Y mod 2^32) * 2^32
+    const u64 yhi = (u64)((long long)Y >> 32);     // floor(Y / 2^32), sign-extended
+    const u64 xhi = (u64)((long long)X >> 63);     // 0 or -1
+    const u64 lo = X + ylo;
+    u64 hi = xhi + yhi + (lo < ylo ? 1u : 0u);
+    const u64 bias_lo = 16ull - (1ull << 36);      // 16 p = 15 * 2^64 + (2^64 - 2^36 + 16)
+    const u64 lo2 = lo + bias_lo;
+    hi += 15u + (lo2 < bias_lo ? 1u : 0u);
+    // hi in [1, 24]: lo2 + hi * (2^32 - 1), one possible wrap
+#if defined(__CUDA_ARCH__)
+    return canon(add_eps_mul(lo2, (u32)hi));
+#else
+    return canon(reduce128(lo2, hi));  // (host pass of nvcc only: never called)
+#endif
+}
 SR_D u64 acc_reduce(const Acc& A) {
-    u64 c = (u64)A.e1 + A.o1;
-    const u32 l0 = A.e0, l1 = (u32)c;
-    c = (c >> 32) + (u64)A.e2 + A.o2;
-    const u32 l2 = (u32)c;
-    c = (c >> 32) + (u64)A.e3 + A.o3;
-    const u32 l3 = (u32)c;
-    const u32 l4 = (u32)(c >> 32) + A.e4;
-    // 2^128 = -2^32 (mod p); l4 2^32 <= p - 1 is canonical
-    u64 r = reduce128(mk64(l0, l1), mk64(l2, l3));
-    r = sub(r, (u64)l4 << 32);
-    return canon(r);
+    const u64 X = (u64)A.e0 - A.e2 - A.o2 - A.e3 - A.o3;
+    const u64 Y = (u64)A.e1 + A.o1 + A.e2 + A.o2 - A.e4;
+    return fold_xy(X, Y);
 }
 // canonical residue of (accumulated value) * 2^128, i.e. with the Montgomery factor 2^-64 = 2^128 of a product of two
 // raw limbs folded into the reduction.  With T = 2^32: T^2 = T - 1, T^3 = -1, so T^4 .. T^8 = -T, 1 - T, 1, T, T - 1 and
 //   (l0 + l1 T + l2 T^2 + l3 T^3 + l4 T^4) T^4 = (l2 + l3 T) - l1 (T - 1) - l0 T + l4 (T - 1):
 // three modular additions of canonical terms instead of a reduction followed by a shift-reduction and a negation.
 SR_D u64 acc_reduce_m128(const Acc& A) {
-    u64 c = (u64)A.e1 + A.o1;
-    const u32 l0 = A.e0, l1 = (u32)c;
-    c = (c >> 32) + (u64)A.e2 + A.o2;
-    const u32 l2 = (u32)c;
-    c = (c >> 32) + (u64)A.e3 + A.o3;
-    const u32 l3 = (u32)c;
-    const u32 l4 = (u32)(c >> 32) + A.e4;
-    u64 r = mk64(l2, l3);                  // weak
-    r = sub(r, (u64)l1 * EPS);             // (2^32 - 1)^2 < p: canonical
-    r = sub(r, mk64(0u, l0));              // l0 2^32 <= p - 1: canonical
-    r = add(r, (u64)l4 * EPS);
-    return canon(r);
+    // (X + Y T) T^4 = -T (X + Y T) = Y - (X + Y) T
+    const u64 X = (u64)A.e0 - A.e2 - A.o2 - A.e3 - A.o3;
+    const u64 Y = (u64)A.e1 + A.o1 + A.e2 + A.o2 - A.e4;
+    return fold_xy(Y, (u64)0 - (X + Y));
 }
 #endif
 

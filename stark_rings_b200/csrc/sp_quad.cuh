@@ -1,7 +1,7 @@
 // Starknet-prime ring with FOUR threads per ring element, one butterfly stage at a time over the element's
 // shared-memory row.
 //
-// Why (profiles/r01b_gl_ncu.md, Starknet section): the two-thread kernels (sp_half.cuh) hold eight 256-bit values per
+// Why (profiles/r01b_gl_ncu.md, Starknet section): two-thread kernels (round 1, removed) hold eight 256-bit values per
 // thread, need 168 registers and keep 12 warps per SM; `wait` on the carry chains of the wide multiply-adds is the
 // dominant stall, fewer warps are slower (8 warps: -25%), and more warps are impossible both by registers and by
 // shared memory (two 528-byte rows per element at two threads per element = 14 warps).  Here an element belongs to

@@ -171,59 +171,6 @@ SR_HD void mont_round(u32 (&t)[L + 2], const u32 (&a)[L], u32 bi) {
     t[L] = t[L + 1] + (u32)(c >> 32);
 }
 #if defined(__CUDA_ARCH__)
-// Device path: the same CIOS rounds written as carry chains of 32-bit multiply-adds.  Each round
-// adds a * b_i in two chains of four (lo, hi) pairs -- even limbs of a into the aligned pairs
-// (t0,t1)...(t6,t7), odd limbs into (t1,t2)...(t7,t8) -- which ptxas fuses into IMAD.WIDE.U32
-// with carry, then folds m * p with m = -t0 (p = 1 + 0x11 * 2^192 + 2^27 * 2^224).
-// Bound: a, b < p  =>  t < 2p < 2^253 between rounds and t + a b_i + m p < 2^286, so nine limbs
-// are enough and the chain carries into t8 can never overflow.
-SR_D void mont_round_ptx(u32 (&t)[L + 1], const u32 (&a)[L], u32 bi) {
-    asm volatile(
-        "mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
-        "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
-        "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
-        "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
-        "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
-        "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
-        "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
-        "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
-        "addc.u32        %8, %8, 0;\n\t"
-        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
-        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
-    asm volatile(
-        "mad.lo.cc.u32   %0, %8,  %12, %0;\n\t"
-        "madc.hi.cc.u32  %1, %8,  %12, %1;\n\t"
-        "madc.lo.cc.u32  %2, %9,  %12, %2;\n\t"
-        "madc.hi.cc.u32  %3, %9,  %12, %3;\n\t"
-        "madc.lo.cc.u32  %4, %10, %12, %4;\n\t"
-        "madc.hi.cc.u32  %5, %10, %12, %5;\n\t"
-        "madc.lo.cc.u32  %6, %11, %12, %6;\n\t"
-        "madc.hi.cc.u32  %7, %11, %12, %7;\n\t"
-        : "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
-        : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(bi));
-    // t += m p with m = -t0; afterwards t0 == 0 and the value is shifted down one limb
-    u32 m = 0u - t[0];
-    asm volatile(
-        "add.cc.u32      %0, %0, %9;\n\t"   // t0 + m = 2^32 or 0
-        "addc.cc.u32     %1, %1, 0;\n\t"
-        "addc.cc.u32     %2, %2, 0;\n\t"
-        "addc.cc.u32     %3, %3, 0;\n\t"
-        "addc.cc.u32     %4, %4, 0;\n\t"
-        "addc.cc.u32     %5, %5, 0;\n\t"
-        "madc.lo.cc.u32  %6, %9, 0x11, %6;\n\t"
-        "madc.hi.cc.u32  %7, %9, 0x11, %7;\n\t"
-        "addc.u32        %8, %8, 0;\n\t"
-        "mad.lo.cc.u32   %7, %9, 0x08000000, %7;\n\t"
-        "madc.hi.u32     %8, %9, 0x08000000, %8;\n\t"
-        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8])
-        : "r"(m));
-#pragma unroll
-    for (int k = 0; k < L; k++) t[k] = t[k + 1];
-    t[L] = 0;
-}
-#endif
-
-#if defined(__CUDA_ARCH__)
 // Even/odd carry-save form of the same CIOS round (no register moves): the running value is
 //   T = X + Y * 2^32 + z,   X = limbs 0..8 in even-aligned pairs (0,1)(2,3)(4,5)(6,7),
 //                           Y = limbs 1..8 in odd-aligned pairs  (1,2)(3,4)(5,6)(7,8)   (Y[j] = limb j+1),
@@ -294,7 +241,7 @@ SR_D void mont_round_eo(u32 (&X)[L + 1], u32 (&Y)[L + 1], u32& zlo, u32& zhi, co
 
 // r = a * b * 2^-256 mod p (canonical output for canonical inputs)
 SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
-#if defined(__CUDA_ARCH__) && !defined(SR_SP_MONT_NO_EO)  // even/odd carry-save rounds (default)
+#if defined(__CUDA_ARCH__)  // even/odd carry-save rounds
     u32 X[L + 1], Y[L + 1], zlo = 0, zhi = 0, t[L + 1];
 #pragma unroll
     for (int i = 0; i < L + 1; i++) X[i] = Y[i] = 0;
@@ -311,12 +258,6 @@ SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
             t[j] = (u32)c;
         }
     }
-#elif defined(__CUDA_ARCH__)
-    u32 t[L + 1];
-#pragma unroll
-    for (int i = 0; i < L + 1; i++) t[i] = 0;
-#pragma unroll
-    for (int i = 0; i < L; i++) mont_round_ptx(t, a, b[i]);
 #endif
 #if defined(__CUDA_ARCH__)
     // t < 2p: d = t - p, keep t if that borrowed

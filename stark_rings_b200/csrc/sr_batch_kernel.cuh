@@ -37,59 +37,6 @@ batch_kernel(const u64* a, const u64* b, u64* out, size_t n) {
     }
 }
 
-// Warp-autonomous variant: every warp owns its own 32-element tiles and its own slice of shared
-// memory, and synchronises only with itself (__syncwarp).  The warps of an SM drift apart, so at
-// any time some of them are waiting on HBM while the others keep the integer pipes busy; no CTA
-// barrier ever makes the whole SM wait on the slowest load.
-template <class R, int OP, int WARPS, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
-batch_kernel_warp(const u64* a, const u64* b, u64* out, size_t n) {
-    extern __shared__ uint4 smem_raw[];
-    constexpr bool TWO = (OP == OP_NTT_MUL || OP == OP_RING_MUL);
-    const int warp = threadIdx.x >> 5;
-    u32* sA = reinterpret_cast<u32*>(smem_raw) + warp * (TWO ? 2 : 1) * 32 * R::ROW;
-    u32* sB = sA + 32 * R::ROW;
-    const size_t ntiles = (n + 31) / 32;
-    const size_t wstride = (size_t)gridDim.x * WARPS;
-    for (size_t tile = (size_t)blockIdx.x * WARPS + warp; tile < ntiles; tile += wstride) {
-        const size_t e0 = tile * 32;
-        const int ne = (n - e0 < 32) ? (int)(n - e0) : 32;
-        stage_in_warp<R>(sA, a + e0 * R::WORDS64, ne);
-        if (TWO) stage_in_warp<R>(sB, b + e0 * R::WORDS64, ne);
-        __syncwarp();
-        const int lane = threadIdx.x & 31;
-        if (lane < ne) {
-            u32* rowA = sA + lane * R::ROW;
-            u32* rowB = sB + lane * R::ROW;
-            if (OP == OP_CRT) R::op_crt(rowA);
-            if (OP == OP_ICRT) R::op_icrt(rowA);
-            if (OP == OP_NTT_MUL) R::op_ntt_mul(rowA, rowB);
-            if (OP == OP_RING_MUL) R::op_ring_mul(rowA, rowB);
-        }
-        __syncwarp();
-        stage_out_warp<R>(out + e0 * R::WORDS64, sA, ne);
-        __syncwarp();
-    }
-}
-
-template <class R, int OP, int WARPS, int MINB>
-cudaError_t launch_batch_op_warp(const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms) {
-    auto kern = batch_kernel_warp<R, OP, WARPS, MINB>;
-    const bool two = (OP == OP_NTT_MUL || OP == OP_RING_MUL);
-    const size_t smem = (size_t)(two ? 2 : 1) * WARPS * 32 * R::ROW * sizeof(u32);
-    static KernelCache cache;  // per instantiation, per device
-    int blocks_per_sm = 0;
-    cudaError_t e = cache.configure(kern, WARPS * 32, smem, &blocks_per_sm);
-    if (e != cudaSuccess) return e;
-    const size_t ntiles = (n + 31) / 32;
-    if (ntiles == 0) return cudaSuccess;
-    size_t grid = (size_t)sms * blocks_per_sm;
-    const size_t need = (ntiles + WARPS - 1) / WARPS;
-    if (grid > need) grid = need;
-    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(a, b, out, n);
-    return cudaGetLastError();
-}
-
 template <class R, int OP, int T, int MINB>
 cudaError_t launch_batch_op(const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms) {
     auto kern = batch_kernel<R, OP, T, MINB>;

@@ -51,39 +51,6 @@ SR_D void stage_out(u64* __restrict__ g, const u32* __restrict__ s, int ne) {
     }
 }
 
-// Warp-level variants: the 32 lanes of one warp move one 32-element tile.
-template <class R>
-SR_D void stage_in_warp(u32* __restrict__ s, const u64* __restrict__ g, int ne) {
-    const uint4* g4 = reinterpret_cast<const uint4*>(g);
-    const int total = ne * R::CHUNKS;
-    constexpr int U = R::STAGE_UNROLL;
-    int c = threadIdx.x & 31;
-    for (; c + (U - 1) * 32 < total; c += U * 32) {
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) v[u] = ld_stream(g4 + c + u * 32);
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            int cc = c + u * 32, e = cc / R::CHUNKS, j = cc - e * R::CHUNKS;
-            R::put(s + e * R::ROW, j, v[u]);
-        }
-    }
-    for (; c < total; c += 32) {
-        int e = c / R::CHUNKS, j = c - e * R::CHUNKS;
-        R::put(s + e * R::ROW, j, ld_stream(g4 + c));
-    }
-}
-template <class R>
-SR_D void stage_out_warp(u64* __restrict__ g, const u32* __restrict__ s, int ne) {
-    uint4* g4 = reinterpret_cast<uint4*>(g);
-    const int total = ne * R::CHUNKS;
-#pragma unroll 4
-    for (int c = threadIdx.x & 31; c < total; c += 32) {
-        int e = c / R::CHUNKS, j = c - e * R::CHUNKS;
-        st_stream(g4 + c, R::get(s + e * R::ROW, j));
-    }
-}
-
 // Row <-> registers with 128-bit shared-memory accesses
 template <int N>
 SR_D void row_load(u32 (&r)[N], const u32* row) {

@@ -9,7 +9,6 @@
 #include "gl_ring.cuh"
 #include "gl_fused6.cuh"
 #include "sp_quad.cuh"
-#include "sp_half.cuh"
 #include "sp_ring.cuh"
 
 using namespace sr;
@@ -81,7 +80,6 @@ void hc_gl_ring_mul_fused6(const uint64_t* a, const uint64_t* b, uint64_t* out) 
     gl::ring_mul_fused6(rows, rows + 24, 2); memcpy(out, rows, 192);
 }
 void hc_gl_ntt_mul_rolled(uint64_t* a, const uint64_t* b) { gl::ntt_mul_rolled(a, b); }
-uint64_t hc_gl_mul_pow2_rt(uint64_t x, int e) { return gl::canon(gl::mul_pow2_rt(x, e)); }
 
 void hc_sp_crt(uint64_t* e) { sp::Fe c[16]; memcpy(c, e, 512); sp::crt(c); memcpy(e, c, 512); }
 void hc_sp_icrt(uint64_t* e) { sp::Fe c[16]; memcpy(c, e, 512); sp::icrt(c); memcpy(e, c, 512); }
@@ -115,41 +113,6 @@ void hc_sp_ring_mul_quad(const uint64_t* a, const uint64_t* b, uint64_t* out) {
     sp_quad_fwd(ra); sp_quad_fwd(rb);
     for (int t = 0; t < 4; t++) sp::quad_slots(ra, rb, t);
     sp_quad_inv(ra); memcpy(out, ra, 512);
-}
-
-// two-threads-per-element formulation (sp_half.cuh), both halves in sequence
-static void sp_half_crt_host(sp::Fe (&pos)[2][8], const sp::Fe* e) {
-    sp::Fe c[2][8], send[2][4];
-    for (int h = 0; h < 2; h++) {
-        for (int j = 0; j < 8; j++) c[h][j] = e[h + 2 * j];
-        sp::half_crt_local(c[h]);
-        sp::half_crt_send(send[h], c[h], h);
-    }
-    for (int h = 0; h < 2; h++) sp::half_crt_cross(pos[h], c[h], send[1 - h], h);
-}
-static void sp_half_icrt_host(sp::Fe* e, sp::Fe (&pos)[2][8]) {
-    sp::Fe send[2][4], c[2][8];
-    for (int h = 0; h < 2; h++) {
-        sp::half_icrt_first(pos[h], h);
-        sp::half_icrt_send(send[h], pos[h], h);
-    }
-    for (int h = 0; h < 2; h++) {
-        sp::half_icrt_gather(c[h], pos[h], send[1 - h], h);
-        sp::half_icrt_local(c[h]);
-        for (int j = 0; j < 8; j++) e[h + 2 * j] = c[h][j];
-    }
-}
-void hc_sp_crt_half(uint64_t* e) {
-    sp::Fe x[16], pos[2][8]; memcpy(x, e, 512);
-    sp_half_crt_host(pos, x);
-    for (int h = 0; h < 2; h++) for (int q = 0; q < 8; q++) x[8 * h + q] = pos[h][q];
-    memcpy(e, x, 512);
-}
-void hc_sp_icrt_half(uint64_t* e) {
-    sp::Fe x[16], pos[2][8]; memcpy(x, e, 512);
-    for (int h = 0; h < 2; h++) for (int q = 0; q < 8; q++) pos[h][q] = x[8 * h + q];
-    sp_half_icrt_host(x, pos);
-    memcpy(e, x, 512);
 }
 
 }  // extern "C"

@@ -64,12 +64,7 @@ def test_elementwise_against_oracle(hc, name, tag):
             assert np.array_equal(out2, want_rm[i * w:(i + 1) * w]), ("ring_mul_fused6", i)
             x = ea.copy(); hc.hc_gl_ntt_mul_rolled(_p(x), _p(eb))
             assert np.array_equal(x, want_nm[i * w:(i + 1) * w]), ("ntt_mul_rolled", i)
-        if tag == "sp":  # two-threads-per-element formulation (sp_half.cuh)
-            x = ea.copy(); hc.hc_sp_crt_half(_p(x))
-            assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt_half", i)
-            x = ea.copy(); hc.hc_sp_icrt_half(_p(x))
-            assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt_half", i)
-            # four-threads-per-element formulation (sp_quad.cuh)
+        if tag == "sp":  # four-threads-per-element formulation used by the kernels (sp_quad.cuh)
             x = ea.copy(); hc.hc_sp_crt_quad(_p(x))
             assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt_quad", i)
             x = ea.copy(); hc.hc_sp_icrt_quad(_p(x))
@@ -81,15 +76,3 @@ def test_elementwise_against_oracle(hc, name, tag):
             out2 = np.zeros(w, dtype=np.uint64)
             hc.hc_bb_ring_mul_half(_p(ea), _p(eb), _p(out2))
             assert np.array_equal(out2, want_rm[i * w:(i + 1) * w]), ("ring_mul_half", i)
-
-
-def test_gl_runtime_power_of_two(hc):
-    """gl::mul_pow2_rt (runtime, warp-uniform exponent) == x * 2^e mod p for every exponent the tables use."""
-    p = O.MODELS["goldilocks"].p
-    hc.hc_gl_mul_pow2_rt.restype = ctypes.c_uint64
-    hc.hc_gl_mul_pow2_rt.argtypes = [ctypes.c_uint64, ctypes.c_int]
-    rng = random.Random(5)
-    xs = [0, 1, p - 1, p, 2**64 - 1, 2**32 - 1, 2**32, 2**63] + [rng.randrange(2**64) for _ in range(40)]
-    for e in range(192):
-        for x in xs:  # weak inputs (any u64) are allowed
-            assert hc.hc_gl_mul_pow2_rt(x, e) == x * pow(2, e, p) % p, (x, e)
