@@ -41,22 +41,22 @@ sp_quad_kernel(const u64* a, const u64* b, u64* out, size_t n) {
             for (int k = 0; k < trips; k++) {
 #pragma unroll 1
                 for (int s = 0; s < 4; s++) {
-                    sp::quad_fwd_stage(rowA + k * delta, wtab, s, t);
+                    sp::quad_fwd_stage<OP == OP_RING_MUL>(rowA + k * delta, wtab, s, t);  // unreduced in the fused product
                     __syncwarp();
                 }
             }
         }
         if (OP == OP_RING_MUL || OP == OP_NTT_MUL) {
-            sp::quad_slots(rowA, rowB, t);
+            sp::quad_slots<OP == OP_RING_MUL>(rowA, rowB, t);
             __syncwarp();
         }
         if (OP == OP_ICRT || OP == OP_RING_MUL) {
 #pragma unroll 1
             for (int s = 0; s < 3; s++) {
-                sp::quad_inv_stage(rowA, wtab, s, t);
+                sp::quad_inv_stage<OP == OP_RING_MUL>(rowA, wtab, s, t);
                 __syncwarp();
             }
-            sp::quad_inv_last(rowA, t);
+            sp::quad_inv_last<OP == OP_RING_MUL>(rowA, t);
         }
         __syncthreads();
         stage_out<R, T>(out + e0 * R::WORDS64, sA, ne);

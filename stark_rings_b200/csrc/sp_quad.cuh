@@ -17,6 +17,17 @@
 // the root W[2^(3-s) + 2^(4-s) rev_s(b)]: 8 | 4, 12 | 2, 10, 6, 14 | 1, 9, 5, 13, 3, 11, 7, 15; the inverse uses
 // W[32 - that] with the stages in the opposite order and ends with the two scaled outputs (1/16, W[24]/16).
 // All functions are __host__ __device__; tests/hostcheck runs the four "threads" of an element in turn.
+//
+// LAZY (the fused ring product only, where no intermediate value is ever stored as a result): values stay UNREDUCED
+// below 2^256 = 31.99 p (sp_ring.cuh: add_nr / sub_kp / mont_mul_nr).  Bounds, in multiples of p:
+//   forward stage s = 0..3   in < 2s + 1   t = w b < 2   out = a + t, a - t + 2p < 2s + 3        (9 after the last)
+//   slot product             x y 2^-256 < 81 / 31.99 + 1 < 3.54
+//   inverse stage 0 (K = 4)  a + b < 7.08,  a - b + 4p < 7.54 -> times w < 2
+//   inverse stage 1 (K = 8)  a + b < 14.16, a - b + 8p < 15.08 -> < 2
+//   inverse stage 2 (K = 16) a + b < 28.32, a - b + 16p < 30.16 -> < 2
+//   last stage               both inputs partially reduced below 4, a + b, a - b + 4p < 8, scaled and canonicalised
+// Per ring product this removes 104 of the 120 conditional subtractions after a Montgomery multiplication and turns
+// the 128 modular additions / subtractions (8 + 9 + 8 selects each) into 8 / 16 plain carry-chain instructions.
 #pragma once
 #include "sp_ring.cuh"
 
@@ -52,6 +63,7 @@ SR_HD int fwd_root(int s, int b) { return (8 >> s) + (16 >> s) * rev_bits(b, s);
 SR_HD void quad_root(Fe& w, const u32* wtab, int k) { quad_ld(w, wtab, k); }
 
 // forward stage s (0..3) of the element in `row`, thread t (0..3): butterflies 2t, 2t + 1
+template <bool LAZY = false>
 SR_HD void quad_fwd_stage(u32* row, const u32* wtab, int s, int t) {
     const int S = 8 >> s;
     Fe a[2], b[2], w[2], m[2];
@@ -65,17 +77,26 @@ SR_HD void quad_fwd_stage(u32* row, const u32* wtab, int s, int t) {
         quad_root(w[u], wtab, fwd_root(s, blk));
     }
 #pragma unroll
-    for (int u = 0; u < 2; u++) mont_mul(m[u], b[u], w[u]);
+    for (int u = 0; u < 2; u++) {
+        if (LAZY) mont_mul_nr(m[u], b[u], w[u]);
+        else mont_mul(m[u], b[u], w[u]);
+    }
 #pragma unroll
     for (int u = 0; u < 2; u++) {
         Fe x, y;
-        add(x, a[u], m[u]);
-        sub(y, a[u], m[u]);
+        if (LAZY) {
+            add_nr(x, a[u], m[u]);
+            sub_kp(y, a[u], m[u], 2);
+        } else {
+            add(x, a[u], m[u]);
+            sub(y, a[u], m[u]);
+        }
         quad_st(row, idx[u], x);
         quad_st(row, idx[u] + S, y);
     }
 }
 // inverse stage s (0..2: span 1 << s): (a, b) <- (a + b, w (a - b)) with w = W[32 - forward root of that span]
+template <bool LAZY = false>
 SR_HD void quad_inv_stage(u32* row, const u32* wtab, int s, int t) {
     const int S = 1 << s;
     Fe a[2], b[2], w[2], d[2];
@@ -91,18 +112,25 @@ SR_HD void quad_inv_stage(u32* row, const u32* wtab, int s, int t) {
 #pragma unroll
     for (int u = 0; u < 2; u++) {
         Fe x;
-        add(x, a[u], b[u]);
-        sub(d[u], a[u], b[u]);
+        if (LAZY) {
+            add_nr(x, a[u], b[u]);
+            sub_kp(d[u], a[u], b[u], 4u << s);
+        } else {
+            add(x, a[u], b[u]);
+            sub(d[u], a[u], b[u]);
+        }
         quad_st(row, idx[u], x);
     }
 #pragma unroll
     for (int u = 0; u < 2; u++) {
         Fe y;
-        mont_mul(y, d[u], w[u]);
+        if (LAZY) mont_mul_nr(y, d[u], w[u]);
+        else mont_mul(y, d[u], w[u]);
         quad_st(row, idx[u] + S, y);
     }
 }
-// last inverse stage (span 8) with the scalings 1/16 and W[24]/16 (ntt.rs:332-345)
+// last inverse stage (span 8) with the scalings 1/16 and W[24]/16 (ntt.rs:332-345); output canonical
+template <bool LAZY = false>
 SR_HD void quad_inv_last(u32* row, int t) {
 #pragma unroll
     for (int u = 0; u < 2; u++) {
@@ -110,8 +138,16 @@ SR_HD void quad_inv_last(u32* row, int t) {
         Fe a, b, s, d, x, y;
         quad_ld(a, row, i);
         quad_ld(b, row, i + 8);
-        add(s, a, b);
-        sub(d, a, b);
+        if (LAZY) {
+            Fe ar, br;
+            partial_reduce(ar, a);
+            partial_reduce(br, b);
+            add_nr(s, ar, br);
+            sub_kp(d, ar, br, 4);
+        } else {
+            add(s, a, b);
+            sub(d, a, b);
+        }
         mul_scale<0>(x, s);
         mul_scale<1>(y, d);
         quad_st(row, i, x);
@@ -119,13 +155,15 @@ SR_HD void quad_inv_last(u32* row, int t) {
     }
 }
 // slot products 4t .. 4t + 3: rowA[k] <- rowA[k] * rowB[k] (ntt_form.rs:159-175 with BaseCRTField = Fq)
+template <bool LAZY = false>
 SR_HD void quad_slots(u32* rowA, const u32* rowB, int t) {
 #pragma unroll 2
     for (int u = 0; u < 4; u++) {
         Fe x, y, z;
         quad_ld(x, rowA, 4 * t + u);
         quad_ld(y, rowB, 4 * t + u);
-        mont_mul(z, x, y);
+        if (LAZY) mont_mul_nr(z, x, y);
+        else mont_mul(z, x, y);
         quad_st(rowA, 4 * t + u, z);
     }
 }

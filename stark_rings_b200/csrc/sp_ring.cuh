@@ -239,7 +239,11 @@ SR_D void mont_round_eo(u32 (&X)[L + 1], u32 (&Y)[L + 1], u32& zlo, u32& zhi, co
 }
 #endif
 
-// r = a * b * 2^-256 mod p (canonical output for canonical inputs)
+// r = a * b * 2^-256 mod p.  REDUCE: canonical output (for a b < p 2^256, e.g. canonical inputs).  !REDUCE: the
+// final conditional subtraction is left out and the output is only < 2p -- for a b < p 2^256 still, which unreduced
+// inputs below 32p times a canonical constant, or two inputs below 5.6p, satisfy (p < 2^256 / 31.99); the slot
+// product of two inputs below 9p comes out below 3.6p.
+template <bool REDUCE = true>
 SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
 #if defined(__CUDA_ARCH__)  // even/odd carry-save rounds
     u32 X[L + 1], Y[L + 1], zlo = 0, zhi = 0, t[L + 1];
@@ -260,6 +264,11 @@ SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
     }
 #endif
 #if defined(__CUDA_ARCH__)
+    if (!REDUCE) {
+#pragma unroll
+        for (int i = 0; i < L; i++) r.v[i] = t[i];
+        return;
+    }
     // t < 2p: d = t - p, keep t if that borrowed
     u32 d[L], br;
     asm volatile(
@@ -283,6 +292,11 @@ SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
     for (int i = 0; i < L + 2; i++) t[i] = 0;
 #pragma unroll
     for (int i = 0; i < L; i++) mont_round(t, a, b[i]);
+    if (!REDUCE) {
+#pragma unroll
+        for (int i = 0; i < L; i++) r.v[i] = t[i];
+        return;
+    }
     // t < 2p: conditional subtraction
     u32 d[L];
     u64 br = 0;
@@ -297,7 +311,135 @@ SR_HD void mont_mul_limbs(Fe& r, const u32 (&a)[L], const u32 (&b)[L]) {
     for (int i = 0; i < L; i++) r.v[i] = keep_t ? t[i] : d[i];
 #endif
 }
-SR_HD void mont_mul(Fe& r, const Fe& a, const Fe& b) { mont_mul_limbs(r, a.v, b.v); }
+SR_HD void mont_mul(Fe& r, const Fe& a, const Fe& b) { mont_mul_limbs<true>(r, a.v, b.v); }
+SR_HD void mont_mul_nr(Fe& r, const Fe& a, const Fe& b) { mont_mul_limbs<false>(r, a.v, b.v); }
+
+// ---- unreduced ("lazy") arithmetic of the fused ring product ------------------------------------------------
+// Values are only kept below 2^256 (31.99 p): sums are plain 256-bit additions, differences get a multiple of p
+// added instead of a conditional correction, products skip the final subtraction.  The bounds are tracked statically
+// in sp_quad.cuh; the host build (tests/hostcheck) checks every one of them at run time.
+// r = a + b (the caller guarantees a + b < 2^256)
+SR_HD void add_nr(Fe& r, const Fe& a, const Fe& b) {
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32   %0, %8,  %16;\n\t"
+        "addc.cc.u32  %1, %9,  %17;\n\t"
+        "addc.cc.u32  %2, %10, %18;\n\t"
+        "addc.cc.u32  %3, %11, %19;\n\t"
+        "addc.cc.u32  %4, %12, %20;\n\t"
+        "addc.cc.u32  %5, %13, %21;\n\t"
+        "addc.cc.u32  %6, %14, %22;\n\t"
+        "addc.u32     %7, %15, %23;\n\t"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+#else
+    u64 c = 0;
+    for (int i = 0; i < L; i++) {
+        c += (u64)a.v[i] + b.v[i];
+        r.v[i] = (u32)c;
+        c >>= 32;
+    }
+    if (c) __builtin_trap();  // bound violated
+#endif
+}
+// r = a - b + K p  (K p >= b and a - b + K p < 2^256 guaranteed by the caller; K <= 16)
+SR_HD void sub_kp(Fe& r, const Fe& a, const Fe& b, u32 K) {
+    const u32 k6 = K * P6, k7 = K * P7;  // K p = K + k6 2^192 + k7 2^224
+#if defined(__CUDA_ARCH__)
+    u32 d[L];
+    asm("sub.cc.u32   %0, %8,  %16;\n\t"
+        "subc.cc.u32  %1, %9,  %17;\n\t"
+        "subc.cc.u32  %2, %10, %18;\n\t"
+        "subc.cc.u32  %3, %11, %19;\n\t"
+        "subc.cc.u32  %4, %12, %20;\n\t"
+        "subc.cc.u32  %5, %13, %21;\n\t"
+        "subc.cc.u32  %6, %14, %22;\n\t"
+        "subc.u32     %7, %15, %23;\n\t"
+        : "=&r"(d[0]), "=&r"(d[1]), "=&r"(d[2]), "=&r"(d[3]), "=&r"(d[4]), "=&r"(d[5]), "=&r"(d[6]), "=&r"(d[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    asm("add.cc.u32   %0, %8,  %16;\n\t"   // the wrap of a - b modulo 2^256 cancels against this carry-out
+        "addc.cc.u32  %1, %9,  0;\n\t"
+        "addc.cc.u32  %2, %10, 0;\n\t"
+        "addc.cc.u32  %3, %11, 0;\n\t"
+        "addc.cc.u32  %4, %12, 0;\n\t"
+        "addc.cc.u32  %5, %13, 0;\n\t"
+        "addc.cc.u32  %6, %14, %17;\n\t"
+        "addc.u32     %7, %15, %18;\n\t"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7])
+        : "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]), "r"(K), "r"(k6), "r"(k7));
+#else
+    // exact integer arithmetic with the bound checks
+    u32 kp[L] = {K, 0, 0, 0, 0, 0, k6, k7};
+    u32 t[L];
+    u64 c = 0;
+    for (int i = 0; i < L; i++) {
+        c += (u64)a.v[i] + kp[i];
+        t[i] = (u32)c;
+        c >>= 32;
+    }
+    if (c) __builtin_trap();  // a + K p < 2^256 is implied by the documented bounds (a - b + K p < 2^256, b small)
+    u64 br = 0;
+    for (int i = 0; i < L; i++) {
+        u64 x = (u64)t[i] - b.v[i] - br;
+        r.v[i] = (u32)x;
+        br = (x >> 63) & 1;
+    }
+    if (br) __builtin_trap();  // K p < b
+#endif
+}
+// x < 2^256  ->  r = x mod p + {2p or 3p-ish}: r = x + 2p - q 2p with q = floor(x / 2^252), which lies in
+// [2p - 2^200, 4p): since 2p = 2^252 + delta (delta < 2^198), x - q 2p = (x mod 2^252) - q delta > -2^202.
+SR_HD void partial_reduce(Fe& r, const Fe& x) {
+    const u32 q = x.v[7] >> 28;  // 0 .. 15
+    // 2p = 2 + 0x22 2^192 + 2^28 2^224
+    Fe two_p;
+    for (int i = 0; i < L; i++) two_p.v[i] = 0;
+    two_p.v[0] = 2; two_p.v[6] = 2 * P6; two_p.v[7] = 2 * P7;
+    Fe q2p;
+    for (int i = 0; i < L; i++) q2p.v[i] = 0;
+    q2p.v[0] = 2 * q; q2p.v[6] = 2 * P6 * q; q2p.v[7] = (2 * P7) * q;  // q 2^28 <= 15 2^28 < 2^32
+    Fe t;
+#if defined(__CUDA_ARCH__)
+    // t = x - q 2p (may wrap), r = t + 2p: the same two chains as sub_kp
+    asm("sub.cc.u32   %0, %8,  %16;\n\t"
+        "subc.cc.u32  %1, %9,  0;\n\t"
+        "subc.cc.u32  %2, %10, 0;\n\t"
+        "subc.cc.u32  %3, %11, 0;\n\t"
+        "subc.cc.u32  %4, %12, 0;\n\t"
+        "subc.cc.u32  %5, %13, 0;\n\t"
+        "subc.cc.u32  %6, %14, %17;\n\t"
+        "subc.u32     %7, %15, %18;\n\t"
+        : "=&r"(t.v[0]), "=&r"(t.v[1]), "=&r"(t.v[2]), "=&r"(t.v[3]), "=&r"(t.v[4]), "=&r"(t.v[5]), "=&r"(t.v[6]), "=&r"(t.v[7])
+        : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]),
+          "r"(q2p.v[0]), "r"(q2p.v[6]), "r"(q2p.v[7]));
+    asm("add.cc.u32   %0, %8,  2;\n\t"
+        "addc.cc.u32  %1, %9,  0;\n\t"
+        "addc.cc.u32  %2, %10, 0;\n\t"
+        "addc.cc.u32  %3, %11, 0;\n\t"
+        "addc.cc.u32  %4, %12, 0;\n\t"
+        "addc.cc.u32  %5, %13, 0;\n\t"
+        "addc.cc.u32  %6, %14, 0x22;\n\t"
+        "addc.u32     %7, %15, 0x10000000;\n\t"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7])
+        : "r"(t.v[0]), "r"(t.v[1]), "r"(t.v[2]), "r"(t.v[3]), "r"(t.v[4]), "r"(t.v[5]), "r"(t.v[6]), "r"(t.v[7]));
+#else
+    u64 c = 0;
+    for (int i = 0; i < L; i++) {  // x + 2p: below 2^256 + 2p, so one extra bit
+        c += (u64)x.v[i] + two_p.v[i];
+        t.v[i] = (u32)c;
+        c >>= 32;
+    }
+    u64 top = c, br = 0;
+    for (int i = 0; i < L; i++) {
+        u64 y = (u64)t.v[i] - q2p.v[i] - br;
+        r.v[i] = (u32)y;
+        br = (y >> 63) & 1;
+    }
+    if (top != br) __builtin_trap();  // the result must be in [0, 2^256)
+    if ((r.v[7] >> 28) >= 4 + 1) __builtin_trap();  // and below 4p < 5 2^252 (loose check)
+#endif
+}
 
 // r = a * ROOTS_OF_UNITY_32[K] (constant in Montgomery form, limbs as immediates)
 template <int K>

@@ -106,6 +106,17 @@ static void sp_quad_inv(uint32_t* row) {
     for (int s = 0; s < 3; s++) for (int t = 0; t < 4; t++) sp::quad_inv_stage(row, wtab, s, t);
     for (int t = 0; t < 4; t++) sp::quad_inv_last(row, t);
 }
+// the unreduced ("lazy") schedule of the fused ring product: every bound is checked at run time (__builtin_trap)
+void hc_sp_ring_mul_quad_lazy(const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    const uint32_t* wtab = &sp::ROOTS_MONT.w[0][0];
+    uint32_t ra[128], rb[128]; memcpy(ra, a, 512); memcpy(rb, b, 512);
+    for (int s = 0; s < 4; s++) for (int t = 0; t < 4; t++) sp::quad_fwd_stage<true>(ra, wtab, s, t);
+    for (int s = 0; s < 4; s++) for (int t = 0; t < 4; t++) sp::quad_fwd_stage<true>(rb, wtab, s, t);
+    for (int t = 0; t < 4; t++) sp::quad_slots<true>(ra, rb, t);
+    for (int s = 0; s < 3; s++) for (int t = 0; t < 4; t++) sp::quad_inv_stage<true>(ra, wtab, s, t);
+    for (int t = 0; t < 4; t++) sp::quad_inv_last<true>(ra, t);
+    memcpy(out, ra, 512);
+}
 void hc_sp_crt_quad(uint64_t* e) { sp_quad_fwd((uint32_t*)e); }
 void hc_sp_icrt_quad(uint64_t* e) { sp_quad_inv((uint32_t*)e); }
 void hc_sp_ring_mul_quad(const uint64_t* a, const uint64_t* b, uint64_t* out) {

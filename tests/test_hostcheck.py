@@ -72,7 +72,33 @@ def test_elementwise_against_oracle(hc, name, tag):
             out4 = np.zeros(w, dtype=np.uint64)
             hc.hc_sp_ring_mul_quad(_p(ea), _p(eb), _p(out4))
             assert np.array_equal(out4, want_rm[i * w:(i + 1) * w]), ("ring_mul_quad", i)
+            out5 = np.zeros(w, dtype=np.uint64)  # the unreduced schedule the fused kernel runs (bounds trap on the host)
+            hc.hc_sp_ring_mul_quad_lazy(_p(ea), _p(eb), _p(out5))
+            assert np.array_equal(out5, want_rm[i * w:(i + 1) * w]), ("ring_mul_quad_lazy", i)
         if tag == "bb":  # two-threads-per-element formulation used by the fused kernel
             out2 = np.zeros(w, dtype=np.uint64)
             hc.hc_bb_ring_mul_half(_p(ea), _p(eb), _p(out2))
             assert np.array_equal(out2, want_rm[i * w:(i + 1) * w]), ("ring_mul_half", i)
+
+
+def test_sp_lazy_bounds_stress(hc):
+    """The unreduced Starknet schedule on many random and adversarial inputs (all p-1, alternating 0 / p-1, single
+    non-zero coefficients): the host build traps on any violated bound, and the result must equal the oracle's."""
+    name, w = "stark_prime", 64
+    M = O.MODELS[name]
+    pm1 = [((M.p - 1) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+    pats = []
+    for mask in (0xFFFF, 0xAAAA, 0x5555, 0x00FF, 0xFF00, 0x0001, 0x8000, 0x0101):
+        e = np.zeros(w, dtype=np.uint64)
+        for c in range(16):
+            if (mask >> c) & 1:
+                e[4 * c:4 * c + 4] = pm1
+        pats.append(e)
+    a = np.concatenate(pats + [rand_raw(name, 1500, 901)])
+    b = np.concatenate(list(reversed(pats)) + [rand_raw(name, 1500, 902)])
+    want = C.ring_mul(name, a, b, threads=4)
+    out = np.zeros(w, dtype=np.uint64)
+    for i in range(a.size // w):
+        ea, eb = a[i * w:(i + 1) * w].copy(), b[i * w:(i + 1) * w].copy()
+        hc.hc_sp_ring_mul_quad_lazy(_p(ea), _p(eb), _p(out))
+        assert np.array_equal(out, want[i * w:(i + 1) * w]), i
