@@ -106,6 +106,24 @@ std::vector<uint64_t> deserialize_limbs(const std::vector<uint8_t>& bytes) {
     return out;
 }
 
+// Add / Sub / Neg / Sum (ntt_form.rs:588-626, 640-654 and the same operators of coeff_form.rs): element-wise on the batch
+template <class C>
+inline void addsub_limbs(int op, std::vector<uint64_t>& a, const std::vector<uint64_t>* b) {
+    if (b && b->size() != a.size()) throw LengthPanic("operands differ in length");
+    auto& c = Context::global();
+    int rc = op == 0 ? sr_add_batch(c.get(), C::ring, a.data(), b->data(), a.size(), SR_HOST)
+           : op == 1 ? sr_sub_batch(c.get(), C::ring, a.data(), b->data(), a.size(), SR_HOST)
+                     : sr_neg_batch(c.get(), C::ring, a.data(), a.size(), SR_HOST);
+    c.check(rc, "add/sub/neg");
+}
+template <class C>
+inline std::vector<uint64_t> sum_limbs(const std::vector<uint64_t>& a) {
+    std::vector<uint64_t> out(C::LIMBS);
+    auto& c = Context::global();
+    c.check(sr_sum_batch(c.get(), C::ring, a.data(), a.size(), out.data(), SR_HOST), "sum");
+    return out;
+}
+
 // A batch of coefficient-form elements over one flat limb buffer (len() == 1: a single element).
 template <class C>
 struct RqPoly {
@@ -126,6 +144,12 @@ struct RqPoly {
                                   SR_HOST), "ring_mul");
         return out;
     }
+    RqPoly& operator+=(const RqPoly& rhs) { addsub_limbs<C>(0, limbs, &rhs.limbs); return *this; }
+    RqPoly& operator-=(const RqPoly& rhs) { addsub_limbs<C>(1, limbs, &rhs.limbs); return *this; }
+    RqPoly operator+(const RqPoly& rhs) const { RqPoly t(*this); t += rhs; return t; }
+    RqPoly operator-(const RqPoly& rhs) const { RqPoly t(*this); t -= rhs; return t; }
+    RqPoly operator-() const { RqPoly t(*this); addsub_limbs<C>(2, t.limbs, nullptr); return t; }
+    RqPoly sum() const { return RqPoly(sum_limbs<C>(limbs)); }
     bool operator==(const RqPoly& o) const { return limbs == o.limbs; }
     // CanonicalSerialize of the batch (coeff_form.rs:154-167): standard-form little-endian bytes, no length prefix
     std::vector<uint8_t> serialize() const { return serialize_limbs<C>(limbs); }
@@ -153,6 +177,13 @@ struct RqNTT {
     }
     RqNTT operator*(const RqNTT& rhs) const { RqNTT t(*this); t *= rhs; return t; }
     RqNTT mul_unchecked(const RqNTT& rhs) const { return *this * rhs; }  // ntt_form.rs:177-189
+    RqNTT& operator+=(const RqNTT& rhs) { addsub_limbs<C>(0, limbs, &rhs.limbs); return *this; }
+    RqNTT& operator-=(const RqNTT& rhs) { addsub_limbs<C>(1, limbs, &rhs.limbs); return *this; }
+    RqNTT operator+(const RqNTT& rhs) const { RqNTT t(*this); t += rhs; return t; }
+    RqNTT operator-(const RqNTT& rhs) const { RqNTT t(*this); t -= rhs; return t; }
+    RqNTT operator-() const { RqNTT t(*this); addsub_limbs<C>(2, t.limbs, nullptr); return t; }
+    RqNTT sum() const { return RqNTT(sum_limbs<C>(limbs)); }
+    static constexpr size_t dimension() { return C::D; }
     bool operator==(const RqNTT& o) const { return limbs == o.limbs; }
     // every element of the batch *= r, r one element (the body of MulAssign<&R> for the matrix types)
     void scale(const RqNTT& r) {

@@ -494,15 +494,15 @@ matvec_empty_kernel(size_t nrows, size_t row0, MvTail tail) {
     mv_tail<S>(tail, nrows, row0, rb, red, sflag);
 }
 
-#ifndef SR_GLK_NS
-#define SR_GLK_NS 4
-#endif
-#ifndef SR_GLK_CS
-#define SR_GLK_CS 128
-#endif
-#ifndef SR_GLK_SPT
-#define SR_GLK_SPT 2
-#endif
+// CTA shapes of the Goldilocks kernel per number of rows in the pass (B200, m = 2^20, graph-replayed commitments,
+// profiles/r02_matvec_tuning.md): <rows, stages, slots per row group, slots per thread>.  Four rows: 64 threads per
+// row and four slots per thread, two 256-thread CTAs per SM: 0.767 of the HBM roofline against 0.670 for one
+// 512-thread CTA with two slots per thread (more independent work per thread, half the per-chunk overhead per slot,
+// and two CTAs that are never in the same phase).
+#define SR_GLK_SHAPE_1 1, 3, 64, 4
+#define SR_GLK_SHAPE_2 2, 3, 128, 3
+#define SR_GLK_SHAPE_3 3, 3, 64, 4
+#define SR_GLK_SHAPE_4 4, 3, 64, 4
 template <class S>
 static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
                                    u64* out, void* scratch, unsigned* counters, unsigned* seq, bool pdl,
@@ -524,10 +524,10 @@ static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nr
         } else if (ring == RING_GL) {
             const size_t left = nrows - row0;
             const int mg = mv_grid(sms);
-            if (left >= 4) e = gl_k6_launch<4, SR_GLK_NS, SR_GLK_CS, SR_GLK_SPT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
-            else if (left == 3) e = gl_k6_launch<3, SR_GLK_NS, SR_GLK_CS, SR_GLK_SPT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
-            else if (left == 2) e = gl_k6_launch<2, SR_GLK_NS, SR_GLK_CS, SR_GLK_SPT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
-            else e = gl_k6_launch<1, SR_GLK_NS, SR_GLK_CS, SR_GLK_SPT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
+            if (left >= 4) e = gl_k6_launch<SR_GLK_SHAPE_4>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
+            else if (left == 3) e = gl_k6_launch<SR_GLK_SHAPE_3>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
+            else if (left == 2) e = gl_k6_launch<SR_GLK_SHAPE_2>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
+            else e = gl_k6_launch<SR_GLK_SHAPE_1>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
         } else {
             const size_t total = ncols * S::SLOTS;
             int grid = mv_grid(sms);

@@ -11,6 +11,8 @@ extern "C" {
 void sro_crt(int ring, uint64_t* buf, size_t n, int threads);
 void sro_icrt(int ring, uint64_t* buf, size_t n, int threads);
 void sro_ntt_mul(int ring, uint64_t* a, const uint64_t* b, size_t n, int threads);
+void sro_addsub(int ring, int op, uint64_t* a, const uint64_t* b, size_t n);
+void sro_sum(int ring, const uint64_t* in, size_t n, uint64_t* out);
 void sro_ring_mul(int ring, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, int threads);
 int sro_matvec(int ring, const uint64_t* const* rows, size_t kappa, size_t ncols, const uint64_t* v, size_t vlen,
                uint64_t* out, int threads);
@@ -59,6 +61,20 @@ static int run(const char* name) {
     auto want_nm = a;
     sro_ntt_mul(C::ring, want_nm.data(), b.data(), n, 4);
     CHECK((RqNTT<C>(a) * RqNTT<C>(b)).limbs == want_nm);
+    // Add / Sub / Neg / Sum (ntt_form.rs:588-626, 640-654), both forms
+    {
+        auto wa = a, ws = a, wn = a;
+        sro_addsub(C::ring, 0, wa.data(), b.data(), n);
+        sro_addsub(C::ring, 1, ws.data(), b.data(), n);
+        sro_addsub(C::ring, 2, wn.data(), wn.data(), n);
+        std::vector<uint64_t> wsum(C::LIMBS);
+        sro_sum(C::ring, a.data(), n, wsum.data());
+        CHECK((RqNTT<C>(a) + RqNTT<C>(b)).limbs == wa);
+        CHECK((RqPoly<C>(a) - RqPoly<C>(b)).limbs == ws);
+        CHECK((-RqNTT<C>(a)).limbs == wn);
+        CHECK(RqNTT<C>(a).sum().limbs == wsum);
+        CHECK(RqNTT<C>::dimension() == C::D);
+    }
     // fused ring product
     std::vector<uint64_t> want_rm(a.size());
     sro_ring_mul(C::ring, a.data(), b.data(), want_rm.data(), n, 4);
