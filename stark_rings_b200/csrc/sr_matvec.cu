@@ -94,16 +94,14 @@ SR_D void mv_tail(const MvTail& t, size_t nrows, size_t row0, int rb, typename S
         slot0 = (size_t)(epoch % MAILBOX_DEPTH) * ps.nranks;
         dst = ps.slots + (slot0 + ps.rank) * ps.slot_stride;
     }
-    // the last thread makes sure the root has summed the epoch that used this mailbox slot before (one peer load,
-    // overlapped with the summation below)
-    if (tid == T - 1) {
-        int ok = 1;
-        if (mailbox && epoch > (u64)MAILBOX_DEPTH)
-            ok = spin_until(ps.consumed, epoch - MAILBOX_DEPTH, ps.err, ps.timeout_ns) ? 1 : 0;
-        sflag[1] = ok;
-    }
+    // Slot reuse: the root must have summed the epoch that used this mailbox slot before.  One peer load, ISSUED here
+    // and only looked at after the summation below, so that its NVLink round trip is off the critical path.
+    u64 consumed_now = ~0ull;
+    const bool check_slot = mailbox && epoch > (u64)MAILBOX_DEPTH && tid == T - 1;
+    if (check_slot) consumed_now = ld_acquire_sys(ps.consumed);
     // sum the gridDim.x partials of every (row, slot) of this pass: SUB threads per unit, each over a strided
-    // subset, then the SUB sums in order.  Fixed order for a given grid: deterministic.
+    // subset (four independent loads in flight at a time), then the SUB sums in order.  Fixed order for a given
+    // grid: deterministic.
     const int U = rb * S::SLOTS;
     int SUB = T / U;
     if (SUB > 32) SUB = 32;
@@ -112,9 +110,22 @@ SR_D void mv_tail(const MvTail& t, size_t nrows, size_t row0, int rb, typename S
         const int u = tid / SUB, sub = tid - u * SUB;
         const int r = u / S::SLOTS, slot = u - r * S::SLOTS;
         const u64* p = t.partial + (row0 + r) * S::ELEM_U64 + slot * S::SLOT_U64;
+        const size_t stride = nrows * S::ELEM_U64;
         Val s = S::zero();
-        for (int k = sub; k < G; k += SUB) S::acc(s, S::load_cv(p + (size_t)k * nrows * S::ELEM_U64));
+        int k = sub;
+        for (; k + 3 * SUB < G; k += 4 * SUB) {
+            const Val v0 = S::load_cv(p + (size_t)k * stride), v1 = S::load_cv(p + (size_t)(k + SUB) * stride);
+            const Val v2 = S::load_cv(p + (size_t)(k + 2 * SUB) * stride), v3 = S::load_cv(p + (size_t)(k + 3 * SUB) * stride);
+            S::acc(s, v0); S::acc(s, v1); S::acc(s, v2); S::acc(s, v3);
+        }
+        for (; k < G; k += SUB) S::acc(s, S::load_cv(p + (size_t)k * stride));
         red[tid] = s;
+    }
+    if (tid == T - 1) {
+        int ok = 1;
+        if (check_slot && consumed_now < epoch - MAILBOX_DEPTH)
+            ok = spin_until(ps.consumed, epoch - MAILBOX_DEPTH, ps.err, ps.timeout_ns) ? 1 : 0;
+        sflag[1] = ok;
     }
     __syncthreads();
     const int ok = sflag[1];
@@ -502,7 +513,17 @@ matvec_empty_kernel(size_t nrows, size_t row0, MvTail tail) {
 #define SR_GLK_SHAPE_1 1, 3, 64, 4
 #define SR_GLK_SHAPE_2 2, 3, 128, 3
 #define SR_GLK_SHAPE_3 3, 3, 64, 4
-#define SR_GLK_SHAPE_4 4, 3, 64, 4
+#ifndef SR_GLK4_NS  // (overridable for tuning builds: make EXTRA="-DSR_GLK4_NS=4 -DSR_GLK4_CS=128 -DSR_GLK4_SPT=2")
+#define SR_GLK4_NS 3
+#define SR_GLK4_CS 64
+#define SR_GLK4_SPT 4
+#endif
+#define SR_GLK_SHAPE_4 4, SR_GLK4_NS, SR_GLK4_CS, SR_GLK4_SPT
+// Short products (a rank's shard of a sharded commitment): one 512-thread CTA per SM, three slots per thread.  With
+// two CTAs per SM the hand-off tail of a commitment was measured NOT to hide behind the next commitment's column loop
+// (8.3 us exposed per commitment at 2^17 columns per rank against 3.2 us for this shape, 38.2 vs 34.8 us per step).
+#define SR_GLK_SHAPE_4_SHORT 4, 3, 128, 3
+constexpr size_t GLK_SHORT_COLS = (size_t)1 << 19;
 template <class S>
 static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nrows, size_t ncols, const u64* v,
                                    u64* out, void* scratch, unsigned* counters, unsigned* seq, bool pdl,
@@ -524,7 +545,9 @@ static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nr
         } else if (ring == RING_GL) {
             const size_t left = nrows - row0;
             const int mg = mv_grid(sms);
-            if (left >= 4) e = gl_k6_launch<SR_GLK_SHAPE_4>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
+            if (left >= 4 && ncols < GLK_SHORT_COLS)
+                e = gl_k6_launch<SR_GLK_SHAPE_4_SHORT>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
+            else if (left >= 4) e = gl_k6_launch<SR_GLK_SHAPE_4>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
             else if (left == 3) e = gl_k6_launch<SR_GLK_SHAPE_3>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
             else if (left == 2) e = gl_k6_launch<SR_GLK_SHAPE_2>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
             else e = gl_k6_launch<SR_GLK_SHAPE_1>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
