@@ -1,9 +1,9 @@
 """Whole-output oracle comparisons at the BASELINE sizes.
 
-The Goldilocks commit kernels stream 128-slot chunks through a 4-stage TMA ring, two CTAs per SM: a CTA only gets a
-second chunk for m > 4736 columns and only recycles a stage (the `empty` mbarriers, the phase-parity arithmetic) for
-m > 18 944; BASELINE config 4 (m = 2^20) gives every CTA about 221 chunks.  The BabyBear / Starknet kernels wrap their
-grid stride at m > 18 944 / 9 472.  Every case below compares the WHOLE output with the C oracle's mat-vec
+The Goldilocks commit kernel streams 256- / 384-slot chunks through a 3-stage TMA ring, 148 - 888 CTAs depending on
+the row count: a CTA only gets a second chunk and only recycles a stage (the `empty` mbarriers, the phase-parity
+arithmetic) for m of a few tens of thousands of columns; BASELINE config 4 (m = 2^20) gives every CTA 55 - 110
+chunks.  The BabyBear / Starknet kernels wrap their grid stride at m > 18 944 / 9 472.  Every case below compares the WHOLE output with the C oracle's mat-vec
 (reference semantics: linear_algebra/src/matrix.rs:168-178), bit for bit.  The batch kernels are compared on whole
 2^20-element buffers for all three rings."""
 import numpy as np
