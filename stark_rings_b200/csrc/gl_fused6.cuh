@@ -84,18 +84,11 @@ SR_HD void sextic_mul(u64 (&z)[6], const u64 (&x)[6], const u64 (&y)[6], int q) 
     }
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-#if defined(__CUDA_ARCH__)
         Acc d;
-        acc_zero(d);
+        acc_mul(d, x[0], y[k]);
 #pragma unroll
-        for (int i = 0; i < 6; i++) acc_mad(d, x[i], i <= k ? y[k - i] : ry[k + 6 - i]);
+        for (int i = 1; i < 6; i++) acc_mad(d, x[i], i <= k ? y[k - i] : ry[k + 6 - i]);
         z[k] = acc_reduce(d);
-#else
-        u64 acc = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) acc = add(acc, canon(mul(x[i], i <= k ? y[k - i] : ry[k + 6 - i])));
-        z[k] = canon(acc);
-#endif
     }
 }
 
@@ -115,40 +108,51 @@ SR_HD void sextic_products(u64* rowA, const u64* rowB) {
     }
 }
 
-// Last inverse stage (ntt.rs:292-318) on the coefficient pairs (i, i + 12), i in [2 t0, 2 t1), two pairs per trip,
-// with 2^EXTRA folded into the scalings; output canonical.
-template <int EXTRA>
-SR_HD void final_pairs(u64* row, int t0, int t1) {
+#ifndef SR_GL_TAIL4
+#define SR_GL_TAIL4 0  // 1: weak rows take four products per output (no canonicalisation, twice the wide multiply-adds)
+#endif
+// The last two inverse stages (ntt.rs:272-318) in place on the row as constant-coefficient sums (gl_ring.cuh, TailK),
+// two coefficient quadruples (i, i + 6, i + 12, i + 18) per trip.  CANON_IN: the row holds canonical values (sums and
+// differences first, two products per output); otherwise weak values (the subtrahends are canonicalised first; measured
+// against four products per output with no canonicalisation, SR_GL_TAIL4).  Output canonical.
+template <class K, bool CANON_IN>
+SR_HD void tail_rows(u64* row) {
     SR_GL_ROLL
-    for (int t = t0; t < t1; t++) {
-        u64 a[2], b[2], lo[2], hi[2];
-        ld2(row + 2 * t, a[0], a[1]);
-        ld2(row + 12 + 2 * t, b[0], b[1]);
+    for (int t = 0; t < 3; t++) {
+        u64 u0[2], u1[2], u2[2], u3[2], o0[2], o1[2], o2[2], o3[2];
+        ld2(row + 2 * t, u0[0], u0[1]);
+        ld2(row + 6 + 2 * t, u1[0], u1[1]);
+        ld2(row + 12 + 2 * t, u2[0], u2[1]);
+        ld2(row + 18 + 2 * t, u3[0], u3[1]);
 #pragma unroll
         for (int u = 0; u < 2; u++) {
-            const u64 cb = canon(b[u]);
-            const u64 kd = canon(mul(sub(a[u], cb), (u64)SR_GL_KAPPA));
-            // 1/8 and 1/4 of the three-stage inverse become 1/4 = 2^190 and 1/2 = 2^191: one halving stage fewer
-            lo[u] = canon(mul_pow2<(190 + EXTRA) % 192>(sub(add(a[u], cb), kd)));
-            hi[u] = canon(mul_pow2<(191 + EXTRA) % 192>(kd));
+            if (CANON_IN) tail_dot2<K>(o0[u], o1[u], o2[u], o3[u], u0[u], u1[u], u2[u], u3[u]);
+            else if (SR_GL_TAIL4) tail_dot4<K>(o0[u], o1[u], o2[u], o3[u], u0[u], u1[u], u2[u], u3[u]);
+            else tail_dot2<K>(o0[u], o1[u], o2[u], o3[u], u0[u], canon(u1[u]), u2[u], canon(u3[u]));
         }
-        st2(row + 2 * t, lo[0], lo[1]);
-        st2(row + 12 + 2 * t, hi[0], hi[1]);
+        st2(row + 2 * t, o0[0], o0[1]);
+        st2(row + 6 + 2 * t, o1[0], o1[1]);
+        st2(row + 12 + 2 * t, o2[0], o2[1]);
+        st2(row + 18 + 2 * t, o3[0], o3[1]);
     }
 }
-
-// Inverse of crt_stages12 with 2^EXTRA folded into the final scalings, in place on the row.  Input CANONICAL
-// (the sextic products), output canonical.
+// Inverse of crt_stages12 with 2^EXTRA folded into the final scalings: the 1/8 and 1/4 of the three-stage inverse become
+// 1/4 = 2^190 and 1/2 = 2^191 (one halving stage fewer).  Input CANONICAL (the sextic products), output canonical.
 template <int EXTRA>
 SR_HD void icrt_stages12(u64* row) {
+    tail_rows<TailK<(190 + EXTRA) % 192, (191 + EXTRA) % 192>, true>(row);
+}
+// ICRT (ntt.rs:240-319 after the slot isomorphism ntt.rs:385-437) in place on the row: dehomogenisation and the first
+// inverse stage in registers, the last two stages as a loop over the row.  Canonical in, canonical out.
+SR_HD void icrt_row(u64* row) {
     {
-        u64 c[D];
+        u64 c[D], o[D];
         row_load(c, row);
-        ibfly<0, 6, 22, true>(c);   // ntt.rs:272-290
-        ibfly<12, 6, 14, true>(c);
-        row_store(row, c);
+        dehomogenize(o, c);
+        icrt_stage1(o);
+        row_store(row, o);
     }
-    final_pairs<EXTRA>(row, 0, 6);
+    tail_rows<TailK<189, 190>, false>(row);
 }
 
 // NTT-form product (ntt_form.rs:159-175 on raw Montgomery limbs) as a real loop, two slots (48 bytes of each row)

@@ -38,10 +38,7 @@ struct GLPolicy {
         store(rowA, c);
     }
     SR_D static void op_icrt(u32* rowA) {
-        u64 c[24];
-        load(c, rowA);
-        gl::icrt(c);
-        store(rowA, c);
+        gl::icrt_row(reinterpret_cast<u64*>(rowA));
     }
     SR_D static void op_ntt_mul(u32* rowA, const u32* rowB) {
         gl::ntt_mul_rolled(reinterpret_cast<u64*>(rowA), reinterpret_cast<const u64*>(rowB));

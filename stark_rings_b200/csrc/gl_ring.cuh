@@ -39,6 +39,26 @@ constexpr int root_exp(int k) {
     return t[k];
 }
 
+// compile-time arithmetic mod p (constants of the merged inverse stages, icrt_tail)
+constexpr u64 caddm(u64 a, u64 b) {  // a, b < p
+    u64 s = a + b;
+    return (s < a || s >= P) ? s - P : s;
+}
+constexpr u64 csubm(u64 a, u64 b) { return a >= b ? a - b : a + (P - b); }
+constexpr u64 cmulm(u64 a, u64 b) {
+    u64 r = 0;
+    for (int i = 63; i >= 0; i--) {
+        r = caddm(r, r);
+        if ((b >> i) & 1) r = caddm(r, a);
+    }
+    return r;
+}
+constexpr u64 cpow2(int e) {
+    u64 r = 1;
+    for (int i = 0; i < e; i++) r = caddm(r, r);
+    return r;
+}
+
 #if defined(__CUDACC__)
 static __constant__ u32 c_eps = 0xFFFFFFFFu;  // 2^64 mod p as a constant-bank operand (see plus_eps_if)
 #endif
@@ -293,25 +313,19 @@ SR_HD void crt(u64 (&c)[D]) {
 #pragma unroll
     for (int i = 0; i < D; i++) c[i] = canon(o[i]);
 }
-SR_HD void icrt(u64 (&c)[D]) {
-    u64 o[D];
-    dehomogenize(o, c);
-    icrt_stages<0>(o);
-#pragma unroll
-    for (int i = 0; i < D; i++) c[i] = canon(o[i]);
-}
 
-#if defined(__CUDACC__)  // (both nvcc passes: the slot traits of sr_slots.cuh name these types in kernel templates)
 // ---- lazy accumulation of 64 x 64 -> 128-bit products -------------------------------------------
 // The sum is kept UNREDUCED in a 160-bit accumulator held as two interleaved carry-save halves
 // (E: limbs 0..4 takes lo*lo and hi*hi, O: limbs 1..3 takes the two cross products), so every partial
 // product is one IMAD.WIDE.U32 with carry and no modular reduction happens until the end.
+// (The host versions are the same limb arithmetic in portable C, so that tests/hostcheck runs the lazy code paths.)
 struct Acc {
     u32 e0, e1, e2, e3, e4, o1, o2, o3;
 };
-SR_D void acc_zero(Acc& A) { A.e0 = A.e1 = A.e2 = A.e3 = A.e4 = A.o1 = A.o2 = A.o3 = 0; }
-SR_D void acc_mad(Acc& A, u64 a, u64 b) {
+SR_HD void acc_zero(Acc& A) { A.e0 = A.e1 = A.e2 = A.e3 = A.e4 = A.o1 = A.o2 = A.o3 = 0; }
+SR_HD void acc_mad(Acc& A, u64 a, u64 b) {
     const u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
+#if defined(__CUDA_ARCH__)
     asm("mad.lo.cc.u32   %0, %5, %7, %0;\n\t"
         "madc.hi.cc.u32  %1, %5, %7, %1;\n\t"
         "madc.lo.cc.u32  %2, %6, %8, %2;\n\t"
@@ -327,14 +341,39 @@ SR_D void acc_mad(Acc& A, u64 a, u64 b) {
         "addc.u32        %2, %2, 0;\n\t"
         : "+r"(A.o1), "+r"(A.o2), "+r"(A.o3)
         : "r"(al), "r"(ah), "r"(bl), "r"(bh));
+#else
+    const u64 ll = (u64)al * bl, hh = (u64)ah * bh, lh = (u64)al * bh, hl = (u64)ah * bl;
+    u64 lo = mk64(A.e0, A.e1), hi = mk64(A.e2, A.e3), t;
+    t = lo + ll; u64 c = t < lo; lo = t;
+    t = hi + hh; u64 c2 = t < hi; hi = t;
+    t = hi + c; c2 += t < hi; hi = t;
+    A.e0 = (u32)lo; A.e1 = (u32)(lo >> 32); A.e2 = (u32)hi; A.e3 = (u32)(hi >> 32); A.e4 += (u32)c2;
+    u64 o = mk64(A.o1, A.o2);
+    t = o + lh; A.o3 += (u32)(t < o); o = t;
+    t = o + hl; A.o3 += (u32)(t < o); o = t;
+    A.o1 = (u32)o; A.o2 = (u32)(o >> 32);
+#endif
 }
-// canonical residue of the accumulated value; valid while the true sum is < 2^160 (up to 2^32 products).
-// With T = 2^32 (T^2 = T - 1, T^3 = -1, T^4 = -T mod p) the value e0 + (e1+o1) T + (e2+o2) T^2 + (e3+o3) T^3 + e4 T^4
-// is  X + Y T  with  X = e0 - (e2+o2) - (e3+o3)  in (-2^34, 2^32)  and  Y = (e1+o1) + (e2+o2) - e4  in (-2^32, 2^34):
-// two signed 64-bit sums (no carry chain through the limbs, no E/O merge), then V = X + Y T + 16 p > 0 as a 128-bit
-// integer whose small high word is folded with 2^64 = 2^32 - 1.  About half the instructions of the limb-by-limb
-// merge followed by reduce128 / sub / canon.
-SR_D u64 fold_xy(u64 X, u64 Y) {  // X, Y two's-complement 64-bit, |X|, |Y| < 2^35
+// A <- a * b (the first product of a sum: no carries into the top limbs yet)
+SR_HD void acc_mul(Acc& A, u64 a, u64 b) {
+    const u32 al = (u32)a, ah = (u32)(a >> 32), bl = (u32)b, bh = (u32)(b >> 32);
+    const u64 ll = (u64)al * bl, hh = (u64)ah * bh, lh = (u64)al * bh;
+    A.e0 = (u32)ll; A.e1 = (u32)(ll >> 32); A.e2 = (u32)hh; A.e3 = (u32)(hh >> 32); A.e4 = 0;
+#if defined(__CUDA_ARCH__)
+    A.o1 = (u32)lh; A.o2 = (u32)(lh >> 32);
+    asm("mad.lo.cc.u32   %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32  %1, %3, %4, %1;\n\t"
+        "addc.u32        %2, 0, 0;\n\t"
+        : "+r"(A.o1), "+r"(A.o2), "=r"(A.o3)
+        : "r"(ah), "r"(bl));
+#else
+    const u64 o = lh + (u64)ah * bl;
+    A.o1 = (u32)o; A.o2 = (u32)(o >> 32); A.o3 = (u32)(o < lh);
+#endif
+}
+// Signed fold used by acc_reduce_m128: X + Y T for two's-complement X, Y with |X|, |Y| < 2^35, as V = X + Y T + 16 p > 0
+// (a 128-bit integer whose small high word is folded with 2^64 = 2^32 - 1).
+SR_HD u64 fold_xy(u64 X, u64 Y) {  // X, Y two's-complement 64-bit, |X|, |Y| < 2^35
     // V = X + (Y << 32) + 16 p > 0 (|V| < 2^67 + 2^35, 16 p = 2^68 - 2^36 + 16): low 64 bits and the small high word
     const u64 ylo = Y << 32;                       // (Y mod 2^32) * 2^32
     const u64 yhi = (u64)((long long)Y >> 32);     // floor(Y / 2^32), sign-extended
@@ -348,40 +387,149 @@ SR_D u64 fold_xy(u64 X, u64 Y) {  // X, Y two's-complement 64-bit, |X|, |Y| < 2^
 #if defined(__CUDA_ARCH__)
     return canon(add_eps_mul(lo2, (u32)hi));
 #else
-    return canon(reduce128(lo2, hi));  // (host pass of nvcc only: never called)
+    return canon(reduce128(lo2, hi));
 #endif
 }
-SR_D u64 acc_reduce(const Acc& A) {
-    const u64 X = (u64)A.e0 - A.e2 - A.o2 - A.e3 - A.o3;
-    const u64 Y = (u64)A.e1 + A.o1 + A.e2 + A.o2 - A.e4;
-    return fold_xy(X, Y);
+// Canonical residue of the accumulated value; valid for sums of fewer than 2^31 products.
+// Merge the two halves into limbs l0..l4 (one carry chain), then with T = 2^32, T^2 = 2^64 = 2^32 - 1 and T^3 = -1 (mod p):
+//   l0 + l1 T + l2 T^2 + (l3 + l4 T) T^3  =  [(l0, l1) + l2 (2^32 - 1)]  -  (l3, l4)
+// i.e. one multiply-add fold of the third limb and ONE modular subtraction of the 64-bit number (l3, l4), which is
+// canonical because l4 (the number of carries out of 2^128) is tiny: 16 instructions, against 26 for the signed
+// X + Y T formulation this replaced.
+SR_HD u64 acc_reduce(const Acc& A) {
+    u32 l1, l2, l3, l4;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32   %0, %4, %7;\n\t"
+        "addc.cc.u32  %1, %5, %8;\n\t"
+        "addc.cc.u32  %2, %6, %9;\n\t"
+        "addc.u32     %3, %10, 0;\n\t"
+        : "=&r"(l1), "=&r"(l2), "=&r"(l3), "=r"(l4)
+        : "r"(A.e1), "r"(A.e2), "r"(A.e3), "r"(A.o1), "r"(A.o2), "r"(A.o3), "r"(A.e4));
+    return canon(sub(add_eps_mul(mk64(A.e0, l1), l2), mk64(l3, l4)));
+#else
+    u64 t = (u64)A.e1 + A.o1;
+    l1 = (u32)t;
+    t = (u64)A.e2 + A.o2 + (t >> 32);
+    l2 = (u32)t;
+    t = (u64)A.e3 + A.o3 + (t >> 32);
+    l3 = (u32)t;
+    l4 = A.e4 + (u32)(t >> 32);
+    return canon(sub(reduce128(mk64(A.e0, l1), (u64)l2), mk64(l3, l4)));
+#endif
 }
 // canonical residue of (accumulated value) * 2^128, i.e. with the Montgomery factor 2^-64 = 2^128 of a product of two
 // raw limbs folded into the reduction.  With T = 2^32: T^2 = T - 1, T^3 = -1, so T^4 .. T^8 = -T, 1 - T, 1, T, T - 1 and
 //   (l0 + l1 T + l2 T^2 + l3 T^3 + l4 T^4) T^4 = (l2 + l3 T) - l1 (T - 1) - l0 T + l4 (T - 1):
 // three modular additions of canonical terms instead of a reduction followed by a shift-reduction and a negation.
-SR_D u64 acc_reduce_m128(const Acc& A) {
+SR_HD u64 acc_reduce_m128(const Acc& A) {
     // (X + Y T) T^4 = -T (X + Y T) = Y - (X + Y) T
     const u64 X = (u64)A.e0 - A.e2 - A.o2 - A.e3 - A.o3;
     const u64 Y = (u64)A.e1 + A.o1 + A.e2 + A.o2 - A.e4;
     return fold_xy(Y, (u64)0 - (X + Y));
 }
-#endif
+// canonical a ka + b kb (+ c kc + d kd): weak inputs, one reduction
+SR_HD u64 dot2(u64 a, u64 ka, u64 b, u64 kb) {
+    Acc d;
+    acc_mul(d, a, ka);
+    acc_mad(d, b, kb);
+    return acc_reduce(d);
+}
+SR_HD u64 dot4(u64 a, u64 ka, u64 b, u64 kb, u64 c, u64 kc, u64 e, u64 ke) {
+    Acc d;
+    acc_mul(d, a, ka);
+    acc_mad(d, b, kb);
+    acc_mad(d, c, kc);
+    acc_mad(d, e, ke);
+    return acc_reduce(d);
+}
+
+// ---- the last two inverse stages as constant-coefficient sums -------------------------------------
+// ntt.rs:272-318: with u0..u3 = c[i], c[6+i], c[12+i], c[18+i] after the first inverse stage,
+//   a  = u0 + u1,  a' = w22 (u0 - u1),  b = u2 + u3,  b' = w14 (u2 - u3)           (second stage)
+//   out[i]    = SA (a + b - kappa (a - b))    = A0 (u0 + u1) + A1 (u2 + u3)        A0 = SA (1 - kappa), A1 = SA (1 + kappa)
+//   out[12+i] = SB kappa (a - b)              = B0 (u0 + u1) + B1 (u2 + u3)        B0 = SB kappa, B1 = -B0
+//   out[6+i]  = SA (a' + b' - kappa (a' - b')) = C0 (u0 - u1) + C1 (u2 - u3)       C0 = A0 w22, C1 = A1 w14
+//   out[18+i] = SB kappa (a' - b')            = D0 (u0 - u1) + D1 (u2 - u3)        D0 = B0 w22, D1 = B1 w14
+// (SA, SB: the final scalings 1/8, 1/4 times any extra power of two).  Each output is one lazy sum of 64 x 64 products and ONE
+// reduction, instead of a butterfly (two canonicalisations, add, sub, shift-reduction), the multiplication by kappa with
+// its own reduction, two more shift-reductions and the final canonicalisations: the inverse transform's last stage
+// was 45% of the instructions of the ICRT kernel, all on the ALU pipe, which bounds it.
+template <int EA, int EB>
+struct TailK {
+    static constexpr u64 KAP = SR_GL_KAPPA;
+    static constexpr u64 SA = cpow2(EA), SB = cpow2(EB);
+    static constexpr u64 W22 = cpow2(root_exp(22)), W14 = cpow2(root_exp(14));
+    static constexpr u64 A0 = cmulm(SA, csubm(1, KAP)), A1 = cmulm(SA, caddm(1, KAP));
+    static constexpr u64 B0 = cmulm(SB, KAP), B1 = P - B0;
+    static constexpr u64 C0 = cmulm(A0, W22), C1 = cmulm(A1, W14);
+    static constexpr u64 D0 = cmulm(B0, W22), D1 = cmulm(B1, W14);
+};
+// weak u0..u3 -> the four canonical outputs; four products per output, no additions on 64-bit residues
+template <class K>
+SR_HD void tail_dot4(u64& o0, u64& o1, u64& o2, u64& o3, u64 u0, u64 u1, u64 u2, u64 u3) {
+    o0 = dot4(u0, K::A0, u1, K::A0, u2, K::A1, u3, K::A1);
+    o1 = dot4(u0, K::C0, u1, P - K::C0, u2, K::C1, u3, P - K::C1);
+    o2 = dot4(u0, K::B0, u1, K::B0, u2, K::B1, u3, K::B1);
+    o3 = dot4(u0, K::D0, u1, P - K::D0, u2, K::D1, u3, P - K::D1);
+}
+// u0, u2 weak, u1, u3 CANONICAL -> the four canonical outputs; sums and differences first, two products per output
+template <class K>
+SR_HD void tail_dot2(u64& o0, u64& o1, u64& o2, u64& o3, u64 u0, u64 u1, u64 u2, u64 u3) {
+    const u64 s01 = add(u0, u1), d01 = sub(u0, u1), s23 = add(u2, u3), d23 = sub(u2, u3);
+    o0 = dot2(s01, K::A0, s23, K::A1);
+    o1 = dot2(d01, K::C0, d23, K::C1);
+    o2 = dot2(s01, K::B0, s23, K::B1);
+    o3 = dot2(d01, K::D0, d23, K::D1);
+}
+
+// one butterfly of the first inverse stage; CA / CB: the operand is already canonical (or == p)
+template <int K, bool CA, bool CB>
+SR_HD void ibfly1(u64& x, u64& y) {
+    constexpr int E = root_exp(K);
+    const u64 a = x, b = y;
+    const u64 ca = CA ? a : canon(a), cb = CB ? b : canon(b);
+    x = add(a, cb);
+    y = mul_pow2<E % 96>((E >= 96) ? sub(b, ca) : sub(a, cb));
+}
+
+// first inverse stage (ntt.rs:250-270) on dehomogenised values: copies are canonical, negations canonical or p,
+// twiddled values weak
+SR_HD void icrt_stage1(u64 (&o)[D]) {
+    ibfly1<23, true, true>(o[0], o[3]);
+    ibfly1<23, true, true>(o[1], o[4]);
+    ibfly1<23, true, true>(o[2], o[5]);
+    ibfly1<17, true, true>(o[6], o[9]);
+    ibfly1<17, false, false>(o[7], o[10]);
+    ibfly1<17, false, true>(o[8], o[11]);
+    ibfly1<19, true, true>(o[12], o[15]);
+    ibfly1<19, false, false>(o[13], o[16]);
+    ibfly1<19, false, false>(o[14], o[17]);
+    ibfly1<13, true, true>(o[18], o[21]);
+    ibfly1<13, false, false>(o[19], o[22]);
+    ibfly1<13, false, false>(o[20], o[23]);
+}
+// ntt.rs:240-319 with the slot isomorphism in front (ntt.rs:385-437).  Canonical in, canonical out.
+SR_HD void icrt(u64 (&c)[D]) {
+    u64 o[D];
+    dehomogenize(o, c);
+    icrt_stage1(o);
+    typedef TailK<189, 190> K;
+#pragma unroll
+    for (int i = 0; i < 6; i++) tail_dot4<K>(c[i], c[6 + i], c[12 + i], c[18 + i], o[i], o[6 + i], o[12 + i], o[18 + i]);
+}
 
 // z = x * y in F_p[u]/(u^3 - 2^RHO_EXP), then times 2^POST_EXP.  Weak in, weak out.
-// Device: y1, y2 are pre-multiplied by rho = 2^RHO_EXP (two shift-reductions), after which every output coefficient
+// y1, y2 are pre-multiplied by rho = 2^RHO_EXP (two shift-reductions), after which every output coefficient
 // is one lazy sum of three 64 x 64 products: 9 accumulations and 3 reductions per slot.
 template <int RHO_EXP, int POST_EXP>
 SR_HD void slot_mul(u64* z, const u64* x, const u64* y) {
     const u64 x0 = x[0], x1 = x[1], x2 = x[2], y0 = y[0], y1 = y[1], y2 = y[2];
     u64 c0, c1, c2;
-#if defined(__CUDA_ARCH__)
     const u64 r1 = mul_pow2<RHO_EXP>(y1), r2 = mul_pow2<RHO_EXP>(y2);
     Acc d0, d1, d2;
-    acc_zero(d0); acc_zero(d1); acc_zero(d2);
-    acc_mad(d0, x0, y0); acc_mad(d0, x1, r2); acc_mad(d0, x2, r1);
-    acc_mad(d1, x0, y1); acc_mad(d1, x1, y0); acc_mad(d1, x2, r2);
-    acc_mad(d2, x0, y2); acc_mad(d2, x1, y1); acc_mad(d2, x2, y0);
+    acc_mul(d0, x0, y0); acc_mad(d0, x1, r2); acc_mad(d0, x2, r1);
+    acc_mul(d1, x0, y1); acc_mad(d1, x1, y0); acc_mad(d1, x2, r2);
+    acc_mul(d2, x0, y2); acc_mad(d2, x1, y1); acc_mad(d2, x2, y0);
     if (POST_EXP == 128) {  // the Montgomery factor of a raw-limb product rides on the reduction
         z[0] = acc_reduce_m128(d0);
         z[1] = acc_reduce_m128(d1);
@@ -391,11 +539,6 @@ SR_HD void slot_mul(u64* z, const u64* x, const u64* y) {
     c0 = acc_reduce(d0);
     c1 = acc_reduce(d1);
     c2 = acc_reduce(d2);
-#else
-    c0 = add(mul(x0, y0), mul_pow2<RHO_EXP>(add(mul(x1, y2), mul(x2, y1))));
-    c1 = add(add(mul(x0, y1), mul(x1, y0)), mul_pow2<RHO_EXP>(mul(x2, y2)));
-    c2 = add(add(mul(x0, y2), mul(x1, y1)), mul(x2, y0));
-#endif
     if (POST_EXP != 0) {
         c0 = mul_pow2<POST_EXP>(c0);
         c1 = mul_pow2<POST_EXP>(c1);

@@ -80,6 +80,7 @@ void hc_gl_ring_mul_fused6(const uint64_t* a, const uint64_t* b, uint64_t* out) 
     gl::ring_mul_fused6(rows, rows + 24, 2); memcpy(out, rows, 192);
 }
 void hc_gl_ntt_mul_rolled(uint64_t* a, const uint64_t* b) { gl::ntt_mul_rolled(a, b); }
+void hc_gl_icrt_row(uint64_t* e) { gl::icrt_row(e); }
 
 void hc_sp_crt(uint64_t* e) { sp::Fe c[16]; memcpy(c, e, 512); sp::crt(c); memcpy(e, c, 512); }
 void hc_sp_icrt(uint64_t* e) { sp::Fe c[16]; memcpy(c, e, 512); sp::icrt(c); memcpy(e, c, 512); }

@@ -64,6 +64,8 @@ def test_elementwise_against_oracle(hc, name, tag):
             assert np.array_equal(out2, want_rm[i * w:(i + 1) * w]), ("ring_mul_fused6", i)
             x = ea.copy(); hc.hc_gl_ntt_mul_rolled(_p(x), _p(eb))
             assert np.array_equal(x, want_nm[i * w:(i + 1) * w]), ("ntt_mul_rolled", i)
+            x = ea.copy(); hc.hc_gl_icrt_row(_p(x))  # the row formulation the ICRT kernel runs
+            assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt_row", i)
         if tag == "sp":  # four-threads-per-element formulation used by the kernels (sp_quad.cuh)
             x = ea.copy(); hc.hc_sp_crt_quad(_p(x))
             assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt_quad", i)
