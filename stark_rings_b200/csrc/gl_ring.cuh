@@ -84,8 +84,19 @@ SR_HD u64 canon(u64 x) { return x >= P ? x - P : x; }
 // binding unit of every Goldilocks kernel (profiles/r01b_gl_ncu.md)
 // (EPS comes from constant memory: with an immediate, ptxas strength-reduces the product into a four-instruction
 // shift / subtract / carry sequence, which is exactly what this is meant to avoid.)
-SR_D u64 plus_eps_if(u32 lo, u32 hi, u32 m) {
 #if defined(SR_GL_EPS_ON_ALU)
+#define SR_GL_ADD_ALU 1
+#define SR_GL_AEM_ALU 1
+#endif
+#ifndef SR_GL_ADD_ALU
+#define SR_GL_ADD_ALU 0  // the correction of add() on the ALU pipe
+#endif
+#ifndef SR_GL_AEM_ALU
+#define SR_GL_AEM_ALU 0  // the correction of add_eps_mul() (shift-reductions, accumulator folds) on the ALU pipe
+#endif
+template <bool ON_ALU>
+SR_D u64 plus_eps_if(u32 lo, u32 hi, u32 m) {
+    if (ON_ALU) {
     // kernels whose binding unit is the multiply-add pipe (the mat-vec family) keep the correction on the ALU pipe
     u32 r0, r1;
     asm("sub.cc.u32   %0, %2, %4;\n\t"        // + 2^32 - 1 = - m, + m * 2^32
@@ -94,14 +105,13 @@ SR_D u64 plus_eps_if(u32 lo, u32 hi, u32 m) {
         : "=&r"(r0), "=&r"(r1)
         : "r"(lo), "r"(hi), "r"(m));
     return mk64(r0, r1);
-#else
+    }
     u32 r0, r1;  // the lo / hi pair is what ptxas fuses into one IMAD.WIDE.U32 with a 64-bit addend
     asm("mad.lo.cc.u32   %0, %4, %5, %2;\n\t"
         "madc.hi.u32     %1, %4, %5, %3;\n\t"
         : "=&r"(r0), "=r"(r1)
         : "r"(lo), "r"(hi), "r"(m), "r"(c_eps));
     return mk64(r0, r1);
-#endif
 }
 // a weak, b canonical -> weak
 SR_D u64 add(u64 a, u64 b) {
@@ -111,7 +121,7 @@ SR_D u64 add(u64 a, u64 b) {
         "addc.u32     %2, 0, 0;\n\t"          // m = carry (add-flags are never fed to subc)
         : "=&r"(lo), "=&r"(hi), "=r"(m)
         : "r"((u32)a), "r"((u32)(a >> 32)), "r"((u32)b), "r"((u32)(b >> 32)));
-    return plus_eps_if(lo, hi, m);              // + EPS when the sum wrapped: a + b - 2^64 < p, no second wrap
+    return plus_eps_if<SR_GL_ADD_ALU>(lo, hi, m);  // + EPS when the sum wrapped: a + b - 2^64 < p, no second wrap
 }
 // The same sum with the correction as two PREDICATED adds of 2^32 - 1 (lo + 0xFFFFFFFF, carry into hi): four
 // instructions on the ALU pipe and no multiply-add (the mat-vec kernels, whose wide multiply-add pipe is the
@@ -154,7 +164,7 @@ SR_D u64 add_eps_mul(u64 lo, u32 hl) {
         "addc.u32        %2, 0, 0;\n\t"
         : "=&r"(r0), "=&r"(r1), "=r"(m)
         : "r"((u32)lo), "r"((u32)(lo >> 32)), "r"(hl));
-    return plus_eps_if(r0, r1, m);  // the wrapped sum is < hl * EPS <= 2^64 - 2^33 + 1: adding EPS cannot wrap again
+    return plus_eps_if<SR_GL_AEM_ALU>(r0, r1, m);  // the wrapped sum is < hl * EPS <= 2^64 - 2^33 + 1: adding EPS cannot wrap again
 }
 // (hi, lo) = 128-bit value -> weak residue.  2^64 = 2^32 - 1, 2^96 = -1 (mod p).
 SR_D u64 reduce128(u64 lo, u64 hi) {

@@ -41,7 +41,7 @@ sp_quad_kernel(const u64* a, const u64* b, u64* out, size_t n) {
             for (int k = 0; k < trips; k++) {
 #pragma unroll 1
                 for (int s = 0; s < 4; s++) {
-                    sp::quad_fwd_stage<OP == OP_RING_MUL>(rowA + k * delta, wtab, s, t);  // unreduced in the fused product
+                    sp::quad_fwd_stage<true, OP == OP_CRT>(rowA + k * delta, wtab, s, t);  // unreduced; the CRT canonicalises its last stage
                     __syncwarp();
                 }
             }
@@ -53,10 +53,10 @@ sp_quad_kernel(const u64* a, const u64* b, u64* out, size_t n) {
         if (OP == OP_ICRT || OP == OP_RING_MUL) {
 #pragma unroll 1
             for (int s = 0; s < 3; s++) {
-                sp::quad_inv_stage<OP == OP_RING_MUL>(rowA, wtab, s, t);
+                sp::quad_inv_stage<true>(rowA, wtab, s, t);  // unreduced until the last stage
                 __syncwarp();
             }
-            sp::quad_inv_last<OP == OP_RING_MUL>(rowA, t);
+            sp::quad_inv_last<true>(rowA, t);
         }
         __syncthreads();
         stage_out<R, T>(out + e0 * R::WORDS64, sA, ne);

@@ -18,8 +18,10 @@
 // W[32 - that] with the stages in the opposite order and ends with the two scaled outputs (1/16, W[24]/16).
 // All functions are __host__ __device__; tests/hostcheck runs the four "threads" of an element in turn.
 //
-// LAZY (the fused ring product only, where no intermediate value is ever stored as a result): values stay UNREDUCED
-// below 2^256 = 31.99 p (sp_ring.cuh: add_nr / sub_kp / mont_mul_nr).  Bounds, in multiples of p:
+// LAZY: values stay UNREDUCED below 2^256 = 31.99 p (sp_ring.cuh: add_nr / sub_kp / mont_mul_nr) until they are stored as
+// results.  Used by the fused ring product (bounds below), by the stand-alone CRT (the same forward bounds; the sixteen
+// outputs < 9p are canonicalised in one step each, canon_small) and by the stand-alone ICRT (canonical inputs: every
+// bound of the inverse stages below holds with room to spare).  Bounds, in multiples of p:
 //   forward stage s = 0..3   in < 2s + 1   t = w b < 2   out = a + t, a - t + 2p < 2s + 3        (9 after the last)
 //   slot product             x y 2^-256 < 81 / 31.99 + 1 < 3.54
 //   inverse stage 0 (K = 4)  a + b < 7.08,  a - b + 4p < 7.54 -> times w < 2
@@ -63,7 +65,9 @@ SR_HD int fwd_root(int s, int b) { return (8 >> s) + (16 >> s) * rev_bits(b, s);
 SR_HD void quad_root(Fe& w, const u32* wtab, int k) { quad_ld(w, wtab, k); }
 
 // forward stage s (0..3) of the element in `row`, thread t (0..3): butterflies 2t, 2t + 1
-template <bool LAZY = false>
+// CANON_LAST (with LAZY): the outputs of the last stage (< 9p) are canonicalised in one step before they are stored
+// (the stand-alone CRT, whose results leave the kernel)
+template <bool LAZY = false, bool CANON_LAST = false>
 SR_HD void quad_fwd_stage(u32* row, const u32* wtab, int s, int t) {
     const int S = 8 >> s;
     Fe a[2], b[2], w[2], m[2];
@@ -87,6 +91,10 @@ SR_HD void quad_fwd_stage(u32* row, const u32* wtab, int s, int t) {
         if (LAZY) {
             add_nr(x, a[u], m[u]);
             sub_kp(y, a[u], m[u], 2);
+            if (CANON_LAST && s == 3) {
+                canon_small(x, x);
+                canon_small(y, y);
+            }
         } else {
             add(x, a[u], m[u]);
             sub(y, a[u], m[u]);

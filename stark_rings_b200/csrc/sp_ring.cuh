@@ -441,6 +441,64 @@ SR_HD void partial_reduce(Fe& r, const Fe& x) {
 #endif
 }
 
+// x < 2^256 (in practice the < 9p outputs of the unreduced forward transform)  ->  r = x mod p, canonical, in ONE step:
+// q = floor(x / 2^251) (top limb >> 27, at most 31); since p = 2^251 + delta with delta = 17 2^192 + 1 < 2^197,
+// x - q p = (x mod 2^251) - q delta lies in (-2^202, 2^251): it is the canonical residue, or negative, in which case adding p
+// once gives a value in (p - 2^202, p).  A sparse subtraction chain, the borrow as a mask, a sparse masked addition
+// chain: about the cost of ONE conditional subtraction of the reduced arithmetic, paid once per stored value
+// instead of after every multiplication, addition and subtraction.
+SR_HD void canon_small(Fe& r, const Fe& x) {
+    const u32 q = x.v[7] >> 27;
+    const u32 q6 = q * P6, q7 = q << 27;  // q p = q + q6 2^192 + q7 2^224
+#if defined(__CUDA_ARCH__)
+    u32 t[L], m;
+    asm("sub.cc.u32   %0, %9,  %17;\n\t"
+        "subc.cc.u32  %1, %10, 0;\n\t"
+        "subc.cc.u32  %2, %11, 0;\n\t"
+        "subc.cc.u32  %3, %12, 0;\n\t"
+        "subc.cc.u32  %4, %13, 0;\n\t"
+        "subc.cc.u32  %5, %14, 0;\n\t"
+        "subc.cc.u32  %6, %15, %18;\n\t"
+        "subc.cc.u32  %7, %16, %19;\n\t"
+        "subc.u32     %8, 0, 0;\n\t"          // all ones when x - q p < 0
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(m)
+        : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]),
+          "r"(q), "r"(q6), "r"(q7));
+    const u32 m0 = m & 1u, m6 = m & P6, m7 = m & P7;
+    asm("add.cc.u32   %0, %8,  %16;\n\t"
+        "addc.cc.u32  %1, %9,  0;\n\t"
+        "addc.cc.u32  %2, %10, 0;\n\t"
+        "addc.cc.u32  %3, %11, 0;\n\t"
+        "addc.cc.u32  %4, %12, 0;\n\t"
+        "addc.cc.u32  %5, %13, 0;\n\t"
+        "addc.cc.u32  %6, %14, %17;\n\t"
+        "addc.u32     %7, %15, %18;\n\t"
+        : "=&r"(r.v[0]), "=&r"(r.v[1]), "=&r"(r.v[2]), "=&r"(r.v[3]), "=&r"(r.v[4]), "=&r"(r.v[5]), "=&r"(r.v[6]), "=&r"(r.v[7])
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(m0), "r"(m6), "r"(m7));
+#else
+    const u32 qp[L] = {q, 0, 0, 0, 0, 0, q6, q7};
+    u32 t[L];
+    u64 br = 0;
+    for (int i = 0; i < L; i++) {
+        const u64 y = (u64)x.v[i] - qp[i] - br;
+        t[i] = (u32)y;
+        br = (y >> 63) & 1;
+    }
+    u64 c = 0;
+    for (int i = 0; i < L; i++) {
+        c += (u64)t[i] + (br ? p_limb(i) : 0u);
+        r.v[i] = (u32)c;
+        c >>= 32;
+    }
+    if (c != br) __builtin_trap();  // the correction must bring a negative difference back into [0, 2^256)
+    // the result must be canonical (< p): compare from the top limb down
+    for (int i = L - 1; i >= 0; i--) {
+        if (r.v[i] < p_limb(i)) break;
+        if (r.v[i] > p_limb(i) || i == 0) __builtin_trap();
+    }
+#endif
+}
+
 // r = a * ROOTS_OF_UNITY_32[K] (constant in Montgomery form, limbs as immediates)
 template <int K>
 SR_HD void mulw(Fe& r, const Fe& a) {

@@ -71,6 +71,10 @@ def test_elementwise_against_oracle(hc, name, tag):
             assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt_quad", i)
             x = ea.copy(); hc.hc_sp_icrt_quad(_p(x))
             assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt_quad", i)
+            x = ea.copy(); hc.hc_sp_crt_quad_lazy(_p(x))  # the unreduced schedules the CRT / ICRT kernels run
+            assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt_quad_lazy", i)
+            x = ea.copy(); hc.hc_sp_icrt_quad_lazy(_p(x))
+            assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt_quad_lazy", i)
             out4 = np.zeros(w, dtype=np.uint64)
             hc.hc_sp_ring_mul_quad(_p(ea), _p(eb), _p(out4))
             assert np.array_equal(out4, want_rm[i * w:(i + 1) * w]), ("ring_mul_quad", i)
@@ -99,8 +103,13 @@ def test_sp_lazy_bounds_stress(hc):
     a = np.concatenate(pats + [rand_raw(name, 1500, 901)])
     b = np.concatenate(list(reversed(pats)) + [rand_raw(name, 1500, 902)])
     want = C.ring_mul(name, a, b, threads=4)
+    want_crt, want_icrt = C.crt(name, a.copy()), C.icrt(name, a.copy())
     out = np.zeros(w, dtype=np.uint64)
     for i in range(a.size // w):
         ea, eb = a[i * w:(i + 1) * w].copy(), b[i * w:(i + 1) * w].copy()
         hc.hc_sp_ring_mul_quad_lazy(_p(ea), _p(eb), _p(out))
         assert np.array_equal(out, want[i * w:(i + 1) * w]), i
+        x = ea.copy(); hc.hc_sp_crt_quad_lazy(_p(x))
+        assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt", i)
+        x = ea.copy(); hc.hc_sp_icrt_quad_lazy(_p(x))
+        assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt", i)
