@@ -63,7 +63,9 @@ SR_HD void row_store(u64* row, const u64 (&c)[D]) {
     for (int i = 0; i < D; i += 2) st2(row + i, c[i], c[i + 1]);
 }
 
-// z <- x * y modulo X^6 - rho_q (q warp-uniform); output CANONICAL.
+// z <- x * y modulo X^6 - rho_q (q warp-uniform); output canonical for odd q, weak for even q: the inverse stages
+// (tail_dot2) use quarters 1 and 3 as the canonical operands of their additions and subtractions and accept weak
+// values from quarters 0 and 2.
 // y_1..y_5 are pre-multiplied by rho (five shift-reductions), after which output k is one lazy sum of six products:
 // sum_{i <= k} x_i y_{k-i} + sum_{i > k} x_i (rho y_{k+6-i}).
 SR_HD void sextic_mul(u64 (&z)[6], const u64 (&x)[6], const u64 (&y)[6], int q) {
@@ -88,7 +90,11 @@ SR_HD void sextic_mul(u64 (&z)[6], const u64 (&x)[6], const u64 (&y)[6], int q) 
         acc_mul(d, x[0], y[k]);
 #pragma unroll
         for (int i = 1; i < 6; i++) acc_mad(d, x[i], i <= k ? y[k - i] : ry[k + 6 - i]);
-        z[k] = acc_reduce(d);
+        z[k] = acc_reduce<false>(d);
+    }
+    if (q & 1) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) z[k] = canon(z[k]);
     }
 }
 
@@ -112,8 +118,8 @@ SR_HD void sextic_products(u64* rowA, const u64* rowB) {
 #define SR_GL_TAIL4 0  // 1: weak rows take four products per output (no canonicalisation, twice the wide multiply-adds)
 #endif
 // The last two inverse stages (ntt.rs:272-318) in place on the row as constant-coefficient sums (gl_ring.cuh, TailK),
-// two coefficient quadruples (i, i + 6, i + 12, i + 18) per trip.  CANON_IN: the row holds canonical values (sums and
-// differences first, two products per output); otherwise weak values (the subtrahends are canonicalised first; measured
+// two coefficient quadruples (i, i + 6, i + 12, i + 18) per trip.  CANON_IN: the second and fourth quarter of the row
+// hold canonical values (sums and differences first, two products per output); otherwise weak values (the subtrahends are canonicalised first; measured
 // against four products per output with no canonicalisation, SR_GL_TAIL4).  Output canonical.
 template <class K, bool CANON_IN>
 SR_HD void tail_rows(u64* row) {
@@ -137,7 +143,8 @@ SR_HD void tail_rows(u64* row) {
     }
 }
 // Inverse of crt_stages12 with 2^EXTRA folded into the final scalings: the 1/8 and 1/4 of the three-stage inverse become
-// 1/4 = 2^190 and 1/2 = 2^191 (one halving stage fewer).  Input CANONICAL (the sextic products), output canonical.
+// 1/4 = 2^190 and 1/2 = 2^191 (one halving stage fewer).  Input: the sextic products (quarters 1 and 3 canonical),
+// output canonical.
 template <int EXTRA>
 SR_HD void icrt_stages12(u64* row) {
     tail_rows<TailK<(190 + EXTRA) % 192, (191 + EXTRA) % 192>, true>(row);

@@ -230,6 +230,14 @@ SR_HD u64 mul_pow2(u64 x) {
 #endif
     return K >= 96 ? neg(r) : r;
 }
+// mul_pow2<K> returns a CANONICAL value when its last step is the subtraction of two canonical numbers (sub of
+// canonical operands is canonical): the word-rotation-by-two case, v0 (2^32 - 1) < p minus (v1, v2) < 2^63.
+constexpr bool pow2_canonical(int K) { return K < 96 && K / 32 == 2; }
+template <int K>
+SR_HD u64 mul_pow2c(u64 x) {  // canonical x * 2^K: the canonicalisation is skipped where mul_pow2 already delivers it
+    const u64 r = mul_pow2<K>(x);
+    return pow2_canonical(K) ? r : canon(r);
+}
 template <int K>
 SR_HD u64 mulw(u64 x) {  // x * ROOTS_OF_UNITY_24[K]
     return mul_pow2<root_exp(K)>(x);
@@ -241,7 +249,7 @@ SR_HD void bfly(u64 (&c)[N]) {
     constexpr int E = root_exp(K);
 #pragma unroll
     for (int i = 0; i < SPAN; i++) {
-        const u64 a = c[LO + i], t = canon(mul_pow2<E % 96>(c[LO + SPAN + i]));
+        const u64 a = c[LO + i], t = mul_pow2c<E % 96>(c[LO + SPAN + i]);
         c[LO + i] = (E >= 96) ? sub(a, t) : add(a, t);
         c[LO + SPAN + i] = (E >= 96) ? add(a, t) : sub(a, t);
     }
@@ -267,7 +275,7 @@ SR_HD void crt_stages12(u64 (&c)[D]) {
     for (int i = 0; i < 12; i++) {
         // zeta = ROOTS_OF_UNITY_24[4] = 2^160 = -2^64:  z = -z'  with z' = 2^64 b
         const u64 a = c[i], b = c[12 + i];
-        const u64 zp = canon(mul_pow2<64>(b));
+        const u64 zp = mul_pow2c<64>(b);
         c[i] = sub(a, zp);                 // a + zeta b
         c[12 + i] = add(add(a, b), zp);    // a + b - zeta b
     }
@@ -406,6 +414,7 @@ SR_HD u64 fold_xy(u64 X, u64 Y) {  // X, Y two's-complement 64-bit, |X|, |Y| < 2
 // i.e. one multiply-add fold of the third limb and ONE modular subtraction of the 64-bit number (l3, l4), which is
 // canonical because l4 (the number of carries out of 2^128) is tiny: 16 instructions, against 26 for the signed
 // X + Y T formulation this replaced.
+template <bool CANON = true>
 SR_HD u64 acc_reduce(const Acc& A) {
     u32 l1, l2, l3, l4;
 #if defined(__CUDA_ARCH__)
@@ -415,7 +424,8 @@ SR_HD u64 acc_reduce(const Acc& A) {
         "addc.u32     %3, %10, 0;\n\t"
         : "=&r"(l1), "=&r"(l2), "=&r"(l3), "=r"(l4)
         : "r"(A.e1), "r"(A.e2), "r"(A.e3), "r"(A.o1), "r"(A.o2), "r"(A.o3), "r"(A.e4));
-    return canon(sub(add_eps_mul(mk64(A.e0, l1), l2), mk64(l3, l4)));
+    const u64 r = sub(add_eps_mul(mk64(A.e0, l1), l2), mk64(l3, l4));
+    return CANON ? canon(r) : r;
 #else
     u64 t = (u64)A.e1 + A.o1;
     l1 = (u32)t;

@@ -56,7 +56,7 @@ sp_quad_kernel(const u64* a, const u64* b, u64* out, size_t n) {
                 sp::quad_inv_stage<true>(rowA, wtab, s, t);  // unreduced until the last stage
                 __syncwarp();
             }
-            sp::quad_inv_last<true>(rowA, t);
+            sp::quad_inv_last<true, OP == OP_ICRT>(rowA, t);
         }
         __syncthreads();
         stage_out<R, T>(out + e0 * R::WORDS64, sA, ne);

@@ -138,7 +138,9 @@ SR_HD void quad_inv_stage(u32* row, const u32* wtab, int s, int t) {
     }
 }
 // last inverse stage (span 8) with the scalings 1/16 and W[24]/16 (ntt.rs:332-345); output canonical
-template <bool LAZY = false>
+// SMALL_IN (with LAZY): the inputs are below 8p (the stand-alone ICRT, whose inverse stages start from canonical values:
+// a + b < 2, 4, 8 after stages 0, 1, 2), so that a + b and a - b + 8p stay below 16p without a partial reduction
+template <bool LAZY = false, bool SMALL_IN = false>
 SR_HD void quad_inv_last(u32* row, int t) {
 #pragma unroll
     for (int u = 0; u < 2; u++) {
@@ -146,7 +148,10 @@ SR_HD void quad_inv_last(u32* row, int t) {
         Fe a, b, s, d, x, y;
         quad_ld(a, row, i);
         quad_ld(b, row, i + 8);
-        if (LAZY) {
+        if (LAZY && SMALL_IN) {
+            add_nr(s, a, b);
+            sub_kp(d, a, b, 8);
+        } else if (LAZY) {
             Fe ar, br;
             partial_reduce(ar, a);
             partial_reduce(br, b);

@@ -128,7 +128,7 @@ void hc_sp_icrt_quad_lazy(uint64_t* e) {
     const uint32_t* wtab = &sp::ROOTS_MONT.w[0][0];
     uint32_t* row = (uint32_t*)e;
     for (int s = 0; s < 3; s++) for (int t = 0; t < 4; t++) sp::quad_inv_stage<true>(row, wtab, s, t);
-    for (int t = 0; t < 4; t++) sp::quad_inv_last<true>(row, t);
+    for (int t = 0; t < 4; t++) sp::quad_inv_last<true, true>(row, t);
 }
 void hc_sp_crt_quad(uint64_t* e) { sp_quad_fwd((uint32_t*)e); }
 void hc_sp_icrt_quad(uint64_t* e) { sp_quad_inv((uint32_t*)e); }
