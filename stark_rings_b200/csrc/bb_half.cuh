@@ -20,31 +20,34 @@
 namespace sr {
 namespace bb {
 
+// Twiddles in standard form with their Shoup companions (bb::Tw); only the last stage's coefficients, which also carry
+// the Montgomery 2^-32 of the slot products, stay in Montgomery operand form.
 struct HalfConsts {
-    u32 c1;        // stage 1 multiplier, operand form (x 2^32)
-    u32 w2;        // stage 2 twiddle
-    u32 w3[2];     // stage 3 twiddles (first / second 18-block of the half)
-    u32 rho[4];    // slot moduli r^k_s
-    u32 iw1[2];    // inverse stage 1 twiddles
-    u32 iw2;       // inverse stage 2 twiddle
-    u32 cx, cy;    // last stage: own / partner coefficients (include the Montgomery 2^-32)
+    Tw c1;         // stage 1 multiplier
+    Tw w2;         // stage 2 twiddle
+    Tw w3[2];      // stage 3 twiddles (first / second 18-block of the half)
+    Tw rho[4];     // slot moduli r^k_s
+    Tw iw1[2];     // inverse stage 1 twiddles
+    Tw iw2;        // inverse stage 2 twiddle
+    u32 cx, cy;    // last stage: own / partner coefficients (include the Montgomery 2^-32), operand form (x 2^32)
 };
 
 constexpr u32 csub(u32 a, u32 b) { return a >= b ? a - b : a + P - b; }
 constexpr u32 cadd(u32 a, u32 b) { return (u32)(((u64)a + b) % P); }
+constexpr Tw tw(int k) { return shoup(w_std(k)); }
 
 constexpr HalfConsts half_consts(int h) {
     constexpr u32 kappa = SR_BB_KAPPA_STD, e8 = SR_BB_EIGHT_INV_STD, e4 = SR_BB_FOUR_INV_STD;
     // extra 2^-32: second half of the Montgomery-64 factor of the slot product
     const u32 s8 = cmulmod(e8, R32_INV), s4 = cmulmod(e4, R32_INV);
     if (h == 0)
-        return HalfConsts{w_m32(4), w_m32(2), {w_m32(1), w_m32(7)},
-                          {w_m32(1), w_m32(13), w_m32(7), w_m32(19)},
-                          {w_m32(23), w_m32(17)}, w_m32(22),
+        return HalfConsts{tw(4), tw(2), {tw(1), tw(7)},
+                          {tw(1), tw(13), tw(7), tw(19)},
+                          {tw(23), tw(17)}, tw(22),
                           to_m32(cmulmod(csub(1, kappa), s8)), to_m32(cmulmod(cadd(1, kappa), s8))};
-    return HalfConsts{to_m32(csub(1, w_std(4))), w_m32(10), {w_m32(5), w_m32(11)},
-                      {w_m32(5), w_m32(17), w_m32(11), w_m32(23)},
-                      {w_m32(19), w_m32(13)}, w_m32(14),
+    return HalfConsts{shoup(csub(1, w_std(4))), tw(10), {tw(5), tw(11)},
+                      {tw(5), tw(17), tw(11), tw(23)},
+                      {tw(19), tw(13)}, tw(14),
                       to_m32(cmulmod(csub(0, kappa), s4)), to_m32(cmulmod(kappa, s4))};
 }
 
@@ -62,17 +65,12 @@ SR_HD void half_crt(u32 (&x)[36], const u32* row, const HalfConsts& K) {
 #endif
 #pragma unroll
         for (int t = 0; t < 4; t++) {
-#ifdef SR_BB_STAGE1_FUSED
-            // a + c1 b = red(a 2^32 + b c1'), both products < p^2  (3 wide multiply-adds)
-            x[4 * j + t] = red((u64)a[t] * R32 + (u64)b[t] * K.c1);
-#else
-            x[4 * j + t] = add(a[t], mulc(b[t], K.c1));  // 2 wide multiply-adds + 3 ALU
-#endif
+            x[4 * j + t] = add(a[t], muls(b[t], K.c1));
         }
     }
 #pragma unroll
     for (int i = 0; i < 18; i++) {
-        u32 a = x[i], t = mulc(x[18 + i], K.w2);
+        u32 a = x[i], t = muls(x[18 + i], K.w2);
         x[i] = add(a, t);
         x[18 + i] = sub(a, t);
     }
@@ -80,14 +78,14 @@ SR_HD void half_crt(u32 (&x)[36], const u32* row, const HalfConsts& K) {
     for (int q = 0; q < 2; q++)
 #pragma unroll
         for (int i = 0; i < 9; i++) {
-            u32 a = x[18 * q + i], t = mulc(x[18 * q + 9 + i], K.w3[q]);
+            u32 a = x[18 * q + i], t = muls(x[18 * q + 9 + i], K.w3[q]);
             x[18 * q + i] = add(a, t);
             x[18 * q + 9 + i] = sub(a, t);
         }
 }
 
 // Slot product with a runtime modulus (operand form); see slot_mul_pow.
-SR_HD void slot_mul_rt(u32* z, const u32* x, const u32* y, u32 rho_m32) {
+SR_HD void slot_mul_rt(u32* z, const u32* x, const u32* y, const Tw& rho) {
     u32 yr[SLOT], xv[SLOT], yv[SLOT];
 #pragma unroll
     for (int j = 0; j < SLOT; j++) {
@@ -95,7 +93,7 @@ SR_HD void slot_mul_rt(u32* z, const u32* x, const u32* y, u32 rho_m32) {
         yv[j] = y[j];
     }
 #pragma unroll
-    for (int j = 1; j < SLOT; j++) yr[j] = mulc(yv[j], rho_m32);
+    for (int j = 1; j < SLOT; j++) yr[j] = muls(yv[j], rho);
 #pragma unroll
     for (int k = 0; k < SLOT; k++) {
         u64 acc = 0;
@@ -127,13 +125,13 @@ SR_HD void half_icrt_local(u32 (&x)[36], const HalfConsts& K) {
         for (int i = 0; i < 9; i++) {
             u32 a = x[18 * q + i], b = x[18 * q + 9 + i];
             x[18 * q + i] = add(a, b);
-            x[18 * q + 9 + i] = mulc(a - b + P, K.iw1[q]);
+            x[18 * q + 9 + i] = muls(a - b + P, K.iw1[q]);
         }
 #pragma unroll
     for (int i = 0; i < 18; i++) {
         u32 a = x[i], b = x[18 + i];
         x[i] = add(a, b);
-        x[18 + i] = mulc(a - b + P, K.iw2);
+        x[18 + i] = muls(a - b + P, K.iw2);
     }
 }
 

@@ -155,7 +155,7 @@ SR_HD void icrt_row(u64* row) {
     {
         u64 c[D], o[D];
         row_load(c, row);
-        dehomogenize(o, c);
+        dehomogenize_c(o, c);
         icrt_stage1(o);
         row_store(row, o);
     }

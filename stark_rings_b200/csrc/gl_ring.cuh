@@ -232,7 +232,9 @@ SR_HD u64 mul_pow2(u64 x) {
 }
 // mul_pow2<K> returns a CANONICAL value when its last step is the subtraction of two canonical numbers (sub of
 // canonical operands is canonical): the word-rotation-by-two case, v0 (2^32 - 1) < p minus (v1, v2) < 2^63.
-constexpr bool pow2_canonical(int K) { return K < 96 && K / 32 == 2; }
+// For K >= 96 the result is p - canon(r): canonical, or p itself for a zero input, which add / sub accept as their second
+// operand just the same.
+constexpr bool pow2_canonical(int K) { return K >= 96 || K / 32 == 2; }
 template <int K>
 SR_HD u64 mul_pow2c(u64 x) {  // canonical x * 2^K: the canonicalisation is skipped where mul_pow2 already delivers it
     const u64 r = mul_pow2<K>(x);
@@ -512,26 +514,33 @@ SR_HD void ibfly1(u64& x, u64& y) {
     y = mul_pow2<E % 96>((E >= 96) ? sub(b, ca) : sub(a, cb));
 }
 
-// first inverse stage (ntt.rs:250-270) on dehomogenised values: copies are canonical, negations canonical or p,
-// twiddled values weak
+// dehomogenisation with canonical (or p) outputs: all but one of its twiddles deliver that for free (pow2_canonical)
+SR_HD void dehomogenize_c(u64 (&o)[D], const u64 (&c)[D]) {
+#define MULW(k, x) ::sr::gl::mul_pow2c<::sr::gl::root_exp(k)>(x)
+#define NEG ::sr::gl::neg
+    SR_GL_DEHOMOG(o, c)
+#undef MULW
+#undef NEG
+}
+// first inverse stage (ntt.rs:250-270) on the values of dehomogenize_c (all canonical or p)
 SR_HD void icrt_stage1(u64 (&o)[D]) {
     ibfly1<23, true, true>(o[0], o[3]);
     ibfly1<23, true, true>(o[1], o[4]);
     ibfly1<23, true, true>(o[2], o[5]);
     ibfly1<17, true, true>(o[6], o[9]);
-    ibfly1<17, false, false>(o[7], o[10]);
-    ibfly1<17, false, true>(o[8], o[11]);
+    ibfly1<17, true, true>(o[7], o[10]);
+    ibfly1<17, true, true>(o[8], o[11]);
     ibfly1<19, true, true>(o[12], o[15]);
-    ibfly1<19, false, false>(o[13], o[16]);
-    ibfly1<19, false, false>(o[14], o[17]);
+    ibfly1<19, true, true>(o[13], o[16]);
+    ibfly1<19, true, true>(o[14], o[17]);
     ibfly1<13, true, true>(o[18], o[21]);
-    ibfly1<13, false, false>(o[19], o[22]);
-    ibfly1<13, false, false>(o[20], o[23]);
+    ibfly1<13, true, true>(o[19], o[22]);
+    ibfly1<13, true, true>(o[20], o[23]);
 }
 // ntt.rs:240-319 with the slot isomorphism in front (ntt.rs:385-437).  Canonical in, canonical out.
 SR_HD void icrt(u64 (&c)[D]) {
     u64 o[D];
-    dehomogenize(o, c);
+    dehomogenize_c(o, c);
     icrt_stage1(o);
     typedef TailK<189, 190> K;
 #pragma unroll
