@@ -228,6 +228,55 @@ SR_HD void slot_mul_ntt_lazy(u32* z, const u32* x, const u32* y) {
     for (int j = 0; j < SLOT; j++) z[3 * (j % 3) + j / 3] = zp[j];
 }
 
+// ---- sums of NTT-form slot products (the mat-vec family) -----------------------------------------------------------
+// sum_c a_c * x_c for one slot, with the 64-bit accumulators of slot_mul_pow kept UNREDUCED across the whole sum: the
+// running value of every output coefficient stays below B = p 2^32 (fold of the high word after every second
+// product: B + 2 p^2 < 2 B), one Montgomery reduction pair per coefficient at the very end instead of one reduction
+// and one modular addition per coefficient and product.  The vector operand is prepared once per slot (power order,
+// multiples by rho) and shared by all matrix rows.
+struct SlotPrep {
+    u32 y[SLOT], yr[SLOT];  // power order; yr[j] = rho y[j] (j >= 1)
+};
+struct SlotAcc {
+    u64 d[SLOT];  // power order; invariant: d[k] < p 2^32
+};
+SR_HD void slot_prep_ntt(SlotPrep& p, const u32* x) {  // x: one slot in memory order
+    constexpr Tw rho = shoup(w_std(1));
+#pragma unroll
+    for (int j = 0; j < SLOT; j++) p.y[j] = x[3 * (j % 3) + j / 3];
+    p.yr[0] = 0;
+#pragma unroll
+    for (int j = 1; j < SLOT; j++) p.yr[j] = muls(p.y[j], rho);
+}
+SR_HD void slot_acc_zero(SlotAcc& A) {
+#pragma unroll
+    for (int k = 0; k < SLOT; k++) A.d[k] = 0;
+}
+SR_HD void slot_acc_mad(SlotAcc& A, const u32* a, const SlotPrep& p) {  // a: one slot in memory order
+    u32 x[SLOT];
+#pragma unroll
+    for (int j = 0; j < SLOT; j++) x[j] = a[3 * (j % 3) + j / 3];
+#pragma unroll
+    for (int k = 0; k < SLOT; k++) {
+        u64 acc = A.d[k];
+#pragma unroll
+        for (int i = 0; i < SLOT; i++) {
+            const u32 f = (i <= k) ? p.y[(i <= k) ? k - i : 0] : p.yr[(i <= k) ? 1 : k + SLOT - i];
+            acc += (u64)x[i] * f;
+            if ((i & 1) || i == SLOT - 1) {  // after every second product, and after the last: back below p 2^32
+                u32 hi = (u32)(acc >> 32);
+                hi = umin32(hi, hi - P);
+                acc = ((u64)hi << 32) | (u32)acc;
+            }
+        }
+        A.d[k] = acc;
+    }
+}
+SR_HD void slot_acc_result(u32* z, const SlotAcc& A) {  // z: memory order; both 2^-32 of the Montgomery-64 layout
+#pragma unroll
+    for (int j = 0; j < SLOT; j++) z[3 * (j % 3) + j / 3] = red((u64)red(A.d[j]));
+}
+
 // ntt_form.rs:159-175 on the memory layout: a <- a * b slot-wise (raw Montgomery-64 words).
 SR_HD void ntt_mul(u32 (&a)[D], const u32 (&b)[D]) {
 #pragma unroll

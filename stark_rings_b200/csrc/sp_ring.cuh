@@ -499,6 +499,33 @@ SR_HD void canon_small(Fe& r, const Fe& x) {
 #endif
 }
 
+// ---- sums of products (the mat-vec family): unreduced ------------------------------------------------------------------
+// sum_c a_c x_c with canonical factors: every product skips its final subtraction (mont_mul_nr, < 2p), the running sum
+// is a plain 256-bit addition, and it is brought back below p (canon_small) after every 15 products: p + 15 * 2p = 31p
+// stays below 2^256 = 31.99p.  Saves the conditional subtraction and the modular addition (8 + 9 + 8 selects) of
+// every product.
+struct DotAcc {
+    Fe v;
+    int n;  // products added since v was last canonical
+};
+constexpr int DOT_BURST = 15;
+SR_HD void dot_zero(DotAcc& A) {
+    for (int i = 0; i < L; i++) A.v.v[i] = 0;
+    A.n = 0;
+}
+SR_HD void dot_mad(DotAcc& A, const Fe& a, const Fe& x) {
+    Fe t, s;
+    mont_mul_nr(t, a, x);
+    add_nr(s, A.v, t);
+    A.v = s;
+    if (++A.n == DOT_BURST) {
+        canon_small(s, A.v);
+        A.v = s;
+        A.n = 0;
+    }
+}
+SR_HD void dot_result(Fe& r, const DotAcc& A) { canon_small(r, A.v); }
+
 // r = a * ROOTS_OF_UNITY_32[K] (constant in Montgomery form, limbs as immediates)
 template <int K>
 SR_HD void mulw(Fe& r, const Fe& a) {

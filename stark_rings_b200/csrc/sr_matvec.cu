@@ -375,49 +375,58 @@ static cudaError_t gl_k6_launch(const u64* const* d_rows, size_t nrows, size_t r
 #ifndef SR_MV_RB
 #define SR_MV_RB 4
 #endif
+#ifndef SR_MV_BB_GROUPS
+#define SR_MV_BB_GROUPS 2  // BabyBear: row groups per CTA (matvec_partial_kernel)
+#endif
 constexpr int MV_T = SR_MV_T;  // threads per CTA (multiple of every SLOTS)
 
 // BabyBear / Starknet prime: thread t owns slot (t mod SLOTS) of columns t / SLOTS, t / SLOTS + stride, ...;
 // consecutive threads read consecutive slots, i.e. each warp reads one contiguous span of a row.  Every thread keeps
-// one accumulator per matrix row (RB rows per pass).  Linear factors of the slot product are applied once per
-// accumulated sum instead of per product (S::mul_lazy / S::finish).
-template <class S, int RB>
+// one accumulator per matrix row (RB rows per pass): S::Accum, which for BabyBear is the slot product's nine 64-bit
+// sums kept unreduced over all columns (one reduction pair per coefficient at the end), with the vector operand
+// prepared once per slot and shared by the rows (S::Prep).
+// G thread groups per CTA split the RB rows of the pass between them (BabyBear: two groups of two rows, 36 accumulator
+// registers per thread instead of 72, which keeps two CTAs per SM resident); the groups walk the same slots, so the
+// second group's reads of v hit L1.
+template <class S, int RB, int G>
 __global__ void __launch_bounds__(MV_T)
 matvec_partial_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
                       const u64* __restrict__ v, MvTail tail) {
+    static_assert(RB % G == 0 && MV_T % G == 0 && (MV_T / G) % S::SLOTS == 0, "row groups");
+    constexpr int RPT = RB / G, TG = MV_T / G;  // rows per thread, threads per group
     __shared__ typename S::Val red[MV_T];
     __shared__ int sflag[2];
-    typename S::Val acc[RB];
+    const int grp = threadIdx.x / TG, tl = threadIdx.x % TG;
+    typename S::Accum acc[RPT];
 #pragma unroll
-    for (int r = 0; r < RB; r++) acc[r] = S::zero();
-    const u64* rp[RB];
+    for (int r = 0; r < RPT; r++) S::accum_zero(acc[r]);
+    const u64* rp[RPT];
 #pragma unroll
-    for (int r = 0; r < RB; r++) rp[r] = (row0 + r < nrows) ? rows[row0 + r] : nullptr;
+    for (int r = 0; r < RPT; r++) rp[r] = (row0 + grp * RPT + r < nrows) ? rows[row0 + grp * RPT + r] : nullptr;
 
     const size_t total = ncols * S::SLOTS;  // slots per row
-    const size_t stride = (size_t)gridDim.x * MV_T;
-    for (size_t g = (size_t)blockIdx.x * MV_T + threadIdx.x; g < total; g += stride) {
-        const typename S::Val x = S::load_cached(v + g * S::SLOT_U64);
-        typename S::Val a[RB];
+    const size_t stride = (size_t)gridDim.x * TG;
+    for (size_t g = (size_t)blockIdx.x * TG + tl; g < total; g += stride) {
+        const typename S::Prep x = S::prep(S::load_cached(v + g * S::SLOT_U64));
+        typename S::Val a[RPT];
 #pragma unroll
-        for (int r = 0; r < RB; r++)
+        for (int r = 0; r < RPT; r++)
             if (rp[r]) a[r] = S::load(rp[r] + g * S::SLOT_U64);
 #pragma unroll
-        for (int r = 0; r < RB; r++)
-            if (rp[r]) S::acc(acc[r], S::mul_lazy(a[r], x));
+        for (int r = 0; r < RPT; r++)
+            if (rp[r]) S::accum_mad_p(acc[r], a[r], x);
     }
     pdl_wait();  // the previous kernel on the stream (its tail reads the scratch this one is about to write) is done
     pdl_launch_dependents();
-    // CTA reduction per slot index: thread t holds slot t % SLOTS
+    // CTA reduction per slot index: thread tl of the row's group holds slot tl % SLOTS
 #pragma unroll
     for (int r = 0; r < RB; r++) {
         if (row0 + r >= nrows) break;
-        S::finish(acc[r]);
-        red[threadIdx.x] = acc[r];
+        if (grp == r / RPT) red[tl] = S::accum_result(acc[r % RPT]);
         __syncthreads();
         if (threadIdx.x < S::SLOTS) {
             typename S::Val s = red[threadIdx.x];
-            for (int k = threadIdx.x + S::SLOTS; k < MV_T; k += S::SLOTS) S::acc(s, red[k]);
+            for (int k = threadIdx.x + S::SLOTS; k < TG; k += S::SLOTS) S::acc(s, red[k]);
             S::store(tail.partial + ((size_t)blockIdx.x * nrows + row0 + r) * S::ELEM_U64 + threadIdx.x * S::SLOT_U64, s);
         }
         __syncthreads();
@@ -551,13 +560,23 @@ static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nr
             else if (left == 3) e = gl_k6_launch<SR_GLK_SHAPE_3>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
             else if (left == 2) e = gl_k6_launch<SR_GLK_SHAPE_2>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
             else e = gl_k6_launch<SR_GLK_SHAPE_1>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
-        } else {
+        } else if constexpr (!std::is_same<S, GLSlot>::value) {
+            constexpr int G = std::is_same<S, BBSlot>::value ? SR_MV_BB_GROUPS : 1;
             const size_t total = ncols * S::SLOTS;
             int grid = mv_grid(sms);
-            const size_t need = (total + MV_T - 1) / MV_T;
+            const size_t need = (total + MV_T / G - 1) / (MV_T / G);
             if ((size_t)grid > need) grid = (int)need;
-            e = launch_pdl(matvec_partial_kernel<S, RB>, (unsigned)grid, (unsigned)MV_T, 0, st, pdl, d_rows, nrows, row0,
-                           ncols, v, tail);
+            if (G > 1 && nrows - row0 <= (size_t)(RB / G)) {
+                // the rows left fit one group: every thread takes all of them (no idle group)
+                const size_t need1 = (total + MV_T - 1) / MV_T;
+                int grid1 = mv_grid(sms);
+                if ((size_t)grid1 > need1) grid1 = (int)need1;
+                e = launch_pdl(matvec_partial_kernel<S, RB / G, 1>, (unsigned)grid1, (unsigned)MV_T, 0, st, pdl, d_rows,
+                               nrows, row0, ncols, v, tail);
+            } else {
+                e = launch_pdl(matvec_partial_kernel<S, RB, G>, (unsigned)grid, (unsigned)MV_T, 0, st, pdl, d_rows, nrows,
+                               row0, ncols, v, tail);
+            }
         }
         if (e != cudaSuccess) return e;
         (*launches)++;

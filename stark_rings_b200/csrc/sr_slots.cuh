@@ -44,6 +44,10 @@ struct GLSlot {
         gl::acc_mad(A.d[1], a.c[0], x.c[1]); gl::acc_mad(A.d[1], a.c[1], x.c[0]); gl::acc_mad(A.d[1], a.c[2], r2);
         gl::acc_mad(A.d[2], a.c[0], x.c[2]); gl::acc_mad(A.d[2], a.c[1], x.c[1]); gl::acc_mad(A.d[2], a.c[2], x.c[0]);
     }
+    // Prep: the vector operand prepared once and shared by all rows it multiplies (nothing to prepare here)
+    typedef Val Prep;
+    SR_D static Prep prep(const Val& x) { return x; }
+    SR_D static void accum_mad_p(Accum& A, const Val& a, const Prep& x) { accum_mad(A, a, x); }
     SR_D static Val accum_result(const Accum& A) {  // Montgomery layout: products of raw limbs carry 2^-64 = 2^128
         Val z;
 #pragma unroll
@@ -110,10 +114,14 @@ struct BBSlot {
 #pragma unroll
         for (int i = 0; i < 9; i++) s.c[i] = bb::red((u64)s.c[i]);
     }
-    typedef ValAccum<BBSlot> Accum;
-    SR_D static void accum_zero(Accum& A) { A.v = zero(); }
-    SR_D static void accum_mad(Accum& A, const Val& a, const Val& x) { acc(A.v, mul_lazy(a, x)); }
-    SR_D static Val accum_result(const Accum& A) { Val r = A.v; finish(r); return r; }
+    // Accum: the nine 64-bit accumulators of the slot product kept unreduced over the whole sum (bb::SlotAcc)
+    typedef bb::SlotAcc Accum;
+    typedef bb::SlotPrep Prep;
+    SR_D static Prep prep(const Val& x) { Prep p; bb::slot_prep_ntt(p, x.c); return p; }
+    SR_D static void accum_zero(Accum& A) { bb::slot_acc_zero(A); }
+    SR_D static void accum_mad_p(Accum& A, const Val& a, const Prep& x) { bb::slot_acc_mad(A, a.c, x); }
+    SR_D static void accum_mad(Accum& A, const Val& a, const Val& x) { accum_mad_p(A, a, prep(x)); }
+    SR_D static Val accum_result(const Accum& A) { Val r; bb::slot_acc_result(r.c, A); return r; }
 };
 struct SPSlot {
     static constexpr int SLOTS = 16, SLOT_U64 = 4, ELEM_U64 = 64;
@@ -160,10 +168,14 @@ struct SPSlot {
     SR_D static void acc(Val& s, const Val& x) { Val t; sp::add(t, s, x); s = t; }
     SR_D static Val mul_lazy(const Val& a, const Val& b) { return mul(a, b); }
     SR_D static void finish(Val&) {}
-    typedef ValAccum<SPSlot> Accum;
-    SR_D static void accum_zero(Accum& A) { A.v = zero(); }
-    SR_D static void accum_mad(Accum& A, const Val& a, const Val& x) { acc(A.v, mul(a, x)); }
-    SR_D static Val accum_result(const Accum& A) { return A.v; }
+    // Accum: the running sum kept unreduced (sp::DotAcc: products without their final subtraction, plain additions)
+    typedef sp::DotAcc Accum;
+    typedef Val Prep;
+    SR_D static Prep prep(const Val& x) { return x; }
+    SR_D static void accum_zero(Accum& A) { sp::dot_zero(A); }
+    SR_D static void accum_mad(Accum& A, const Val& a, const Val& x) { sp::dot_mad(A, a, x); }
+    SR_D static void accum_mad_p(Accum& A, const Val& a, const Prep& x) { sp::dot_mad(A, a, x); }
+    SR_D static Val accum_result(const Accum& A) { Val r; sp::dot_result(r, A); return r; }
 };
 
 }  // namespace sr

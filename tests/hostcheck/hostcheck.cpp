@@ -63,6 +63,41 @@ void hc_bb_ring_mul_half(const uint64_t* a, const uint64_t* b, uint64_t* out) {
     }
 }
 
+// lazily accumulated sum of NTT-form slot products (the BabyBear mat-vec family): out = sum_c a[c] * x[c], n elements each
+void hc_bb_dot(const uint64_t* a, const uint64_t* x, size_t n, uint64_t* out) {
+    for (int s = 0; s < 8; s++) {
+        bb::SlotAcc A;
+        bb::slot_acc_zero(A);
+        for (size_t c = 0; c < n; c++) {
+            u32 as[9], xs[9];
+            for (int i = 0; i < 9; i++) { as[i] = (u32)a[72 * c + 9 * s + i]; xs[i] = (u32)x[72 * c + 9 * s + i]; }
+            bb::SlotPrep p;
+            bb::slot_prep_ntt(p, xs);
+            bb::slot_acc_mad(A, as, p);
+            for (int k = 0; k < 9; k++)
+                if (A.d[k] >= ((u64)bb::P << 32)) __builtin_trap();  // the invariant of the unreduced sums
+        }
+        u32 z[9];
+        bb::slot_acc_result(z, A);
+        for (int i = 0; i < 9; i++) out[9 * s + i] = z[i];
+    }
+}
+// unreduced sum of Starknet-prime products (sp::DotAcc, the mat-vec family): out = sum_c a[c] * x[c] slot-wise
+void hc_sp_dot(const uint64_t* a, const uint64_t* x, size_t n, uint64_t* out) {
+    for (int s = 0; s < 16; s++) {
+        sp::DotAcc A;
+        sp::dot_zero(A);
+        for (size_t c = 0; c < n; c++) {
+            sp::Fe fa, fx;
+            memcpy(&fa, a + 64 * c + 4 * s, 32);
+            memcpy(&fx, x + 64 * c + 4 * s, 32);
+            sp::dot_mad(A, fa, fx);
+        }
+        sp::Fe r;
+        sp::dot_result(r, A);
+        memcpy(out + 4 * s, &r, 32);
+    }
+}
 void hc_gl_crt(uint64_t* e) { u64 c[24]; memcpy(c, e, 192); gl::crt(c); memcpy(e, c, 192); }
 void hc_gl_icrt(uint64_t* e) { u64 c[24]; memcpy(c, e, 192); gl::icrt(c); memcpy(e, c, 192); }
 void hc_gl_ntt_mul(uint64_t* a, const uint64_t* b) {

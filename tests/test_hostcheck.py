@@ -113,3 +113,34 @@ def test_sp_lazy_bounds_stress(hc):
         assert np.array_equal(x, want_crt[i * w:(i + 1) * w]), ("crt", i)
         x = ea.copy(); hc.hc_sp_icrt_quad_lazy(_p(x))
         assert np.array_equal(x, want_icrt[i * w:(i + 1) * w]), ("icrt", i)
+
+
+def test_bb_lazy_dot(hc):
+    """The unreduced BabyBear slot-product sums of the mat-vec kernels (bb::SlotAcc) against the oracle's mat-vec, on random
+    columns and on all-(p-1) columns (the largest products); the host build traps when an accumulator leaves its bound."""
+    name, w = "babybear", 72
+    M = O.MODELS[name]
+    n = 300
+    a, x = rand_raw(name, n, 31), rand_raw(name, n, 32)
+    worst = np.array(O.to_raw(M, [M.p - 1] * M.D) * 40, dtype=np.uint64)
+    for aa, xx in ((a, x), (worst, worst), (np.concatenate([worst, a]), np.concatenate([worst, x]))):
+        m = aa.size // w
+        want = C.matvec(name, [aa.copy()], xx.copy(), threads=1)
+        out = np.zeros(w, dtype=np.uint64)
+        hc.hc_bb_dot(_p(aa), _p(xx), ctypes.c_size_t(m), _p(out))
+        assert np.array_equal(out, want), m
+
+
+def test_sp_lazy_dot(hc):
+    """The unreduced Starknet-prime product sums of the mat-vec kernels (sp::DotAcc) against the oracle's mat-vec on random
+    and all-(p-1) columns; the host build traps when the running sum would leave 2^256 or a result is not canonical."""
+    name, w = "stark_prime", 64
+    M = O.MODELS[name]
+    a, x = rand_raw(name, 100, 41), rand_raw(name, 100, 42)
+    worst = np.array(O.to_raw(M, [M.p - 1] * M.D) * 47, dtype=np.uint64)
+    for aa, xx in ((a, x), (worst, worst), (np.concatenate([worst, a]), np.concatenate([worst, x]))):
+        m = aa.size // w
+        want = C.matvec(name, [aa.copy()], xx.copy(), threads=1)
+        out = np.zeros(w, dtype=np.uint64)
+        hc.hc_sp_dot(_p(aa), _p(xx), ctypes.c_size_t(m), _p(out))
+        assert np.array_equal(out, want), m
