@@ -8,6 +8,12 @@ namespace sr {
 // ---- fused ring multiplication, two threads per element (bb_half.cuh) -------------------------
 __constant__ bb::HalfConsts BB_HALF_C[2] = {bb::half_consts(0), bb::half_consts(1)};
 
+#ifndef SR_BB_HALF_WARPS
+#define SR_BB_HALF_WARPS 2
+#endif
+#ifndef SR_BB_HALF_MINB
+#define SR_BB_HALF_MINB 8
+#endif
 template <int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 bb_ring_mul_half_kernel(const u64* a, const u64* b, u64* out, size_t n) {
@@ -27,8 +33,25 @@ bb_ring_mul_half_kernel(const u64* a, const u64* b, u64* out, size_t n) {
         stage_in<R, T>(sB, b + e0 * R::WORDS64, ne);
         __syncthreads();
         u32 A[36], B[36], Y[36];
+#if defined(SR_BB_CRT_LOOP)
+        {   // ONE copy of the forward transform for both operands (opaque trip count): 11 KB less code
+            int trips = 2;
+            asm volatile("" : "+r"(trips));
+#pragma unroll
+            for (int i = 0; i < 36; i++) B[i] = 0;
+            const u32* src = sA + el * R::ROW;
+#pragma unroll 1
+            for (int k = 0; k < trips; k++) {
+#pragma unroll
+                for (int i = 0; i < 36; i++) A[i] = B[i];
+                bb::half_crt(B, src, K);
+                src += (sB - sA);
+            }
+        }
+#else
         bb::half_crt(A, sA + el * R::ROW, K);
         bb::half_crt(B, sB + el * R::ROW, K);
+#endif
         bb::half_slots(B, A, K);
         bb::half_icrt_local(B, K);
 #pragma unroll
@@ -70,7 +93,7 @@ cudaError_t bb_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cu
     case OP_CRT: return launch_batch_op<BBPolicy, OP_CRT, 128, 3>(a, b, out, n, st, sms);
     case OP_ICRT: return launch_batch_op<BBPolicy, OP_ICRT, 128, 3>(a, b, out, n, st, sms);
     case OP_NTT_MUL: return launch_batch_op<BBPolicy, OP_NTT_MUL, 64, 4>(a, b, out, n, st, sms);
-    case OP_RING_MUL: return launch_ring_mul_half<2, 8>(a, b, out, n, st, sms);
+    case OP_RING_MUL: return launch_ring_mul_half<SR_BB_HALF_WARPS, SR_BB_HALF_MINB>(a, b, out, n, st, sms);
     }
     return cudaErrorInvalidValue;
 }

@@ -64,7 +64,7 @@ struct BBPolicy {
         load_slot<S>(x, rowA);
 #pragma unroll
         for (int j = 0; j < 9; j++) y[j] = bs[9 * S + j];
-        bb::slot_mul_pow<bb::w_m32(KS[S])>(z, x, y);
+        bb::slot_mul_pow<bb::w_std(KS[S])>(z, x, y);
 #pragma unroll
         for (int j = 0; j < 9; j++) bs[9 * S + j] = z[j];
     }

@@ -71,9 +71,9 @@ SR_HD u32 muls(u32 a, const Tw& t) {
 }
 
 template <int K>
-SR_HD u32 mulw(u32 a) {
-    constexpr u32 w = w_m32(K);
-    return mulc(a, w);
+SR_HD u32 mulw(u32 a) {  // a * ROOTS_OF_UNITY_24[K], a < 2^32, result canonical
+    constexpr Tw t = shoup(w_std(K));
+    return muls(a, t);
 }
 #define SR_BB_MULW(k, x) ::sr::bb::mulw<k>(x)
 
@@ -126,15 +126,15 @@ SR_HD void icrt_stages(u32 (&c)[D]) {
     ibfly<54, 9, 13>(c);
     ibfly<0, 18, 22>(c);
     ibfly<36, 18, 14>(c);
-    constexpr u32 KAPPA_M = to_m32(SR_BB_KAPPA_STD);
-    constexpr u32 E8_M = to_m32(cmulmod(SR_BB_EIGHT_INV_STD, SCALE_STD));
-    constexpr u32 E4_M = to_m32(cmulmod(SR_BB_FOUR_INV_STD, SCALE_STD));
+    constexpr Tw KAPPA_T = shoup(SR_BB_KAPPA_STD);
+    constexpr Tw E8_T = shoup(cmulmod(SR_BB_EIGHT_INV_STD, SCALE_STD));
+    constexpr Tw E4_T = shoup(cmulmod(SR_BB_FOUR_INV_STD, SCALE_STD));
 #pragma unroll
     for (int i = 0; i < 36; i++) {
         u32 a = c[i], b = c[36 + i];
-        u32 kd = mulc(a - b + P, KAPPA_M);
-        c[i] = mulc(sub(add(a, b), kd), E8_M);
-        c[36 + i] = mulc(kd, E4_M);
+        u32 kd = muls(a - b + P, KAPPA_T);
+        c[i] = muls(sub(add(a, b), kd), E8_T);
+        c[36 + i] = muls(kd, E4_T);
     }
 }
 
@@ -170,14 +170,15 @@ SR_HD void icrt(u32 (&c)[D]) {
 
 // Product of x, y (power order: index j = coefficient of Y^j) in F_p[Y]/(Y^9 - rho), times 2^-32:
 //   z_k = 2^-32 * ( sum_{i+j=k} x_i y_j + rho * sum_{i+j=k+9} x_i y_j ).
-// RHO_M32 = rho * 2^32 mod p.  Inputs canonical, output canonical.
+// RHO_STD = rho (standard form).  Inputs canonical, output canonical.
 // 64-bit accumulation: every product < p^2 < B/2.13 with B = p 2^32; the running sum is kept below
 // 2^64 by folding the high word with min(hi, hi - p) (a subtraction of B when hi >= p).
-template <u32 RHO_M32>
+template <u32 RHO_STD>
 SR_HD void slot_mul_pow(u32 (&z)[SLOT], const u32 (&x)[SLOT], const u32 (&y)[SLOT]) {
+    constexpr Tw rho = shoup(RHO_STD);
     u32 yr[SLOT];  // rho * y_j
 #pragma unroll
-    for (int j = 1; j < SLOT; j++) yr[j] = mulc(y[j], RHO_M32);
+    for (int j = 1; j < SLOT; j++) yr[j] = muls(y[j], rho);
 #pragma unroll
     for (int k = 0; k < SLOT; k++) {
         u64 acc = 0;
@@ -208,7 +209,7 @@ SR_HD void slot_mul_ntt(u32* z, const u32* x, const u32* y) {
         xp[j] = x[3 * (j % 3) + j / 3];
         yp[j] = y[3 * (j % 3) + j / 3];
     }
-    slot_mul_pow<w_m32(1)>(zp, xp, yp);
+    slot_mul_pow<w_std(1)>(zp, xp, yp);
 #pragma unroll
     for (int j = 0; j < SLOT; j++) z[3 * (j % 3) + j / 3] = red((u64)zp[j]);
 }
@@ -223,7 +224,7 @@ SR_HD void slot_mul_ntt_lazy(u32* z, const u32* x, const u32* y) {
         xp[j] = x[3 * (j % 3) + j / 3];
         yp[j] = y[3 * (j % 3) + j / 3];
     }
-    slot_mul_pow<w_m32(1)>(zp, xp, yp);
+    slot_mul_pow<w_std(1)>(zp, xp, yp);
 #pragma unroll
     for (int j = 0; j < SLOT; j++) z[3 * (j % 3) + j / 3] = zp[j];
 }
@@ -296,7 +297,7 @@ SR_HD void fused_slot(u32 (&bs)[D], const u32* as) {
         x[j] = as[SLOT * S + j];
         y[j] = bs[SLOT * S + j];
     }
-    slot_mul_pow<w_m32(KS[S])>(z, x, y);
+    slot_mul_pow<w_std(KS[S])>(z, x, y);
 #pragma unroll
     for (int j = 0; j < SLOT; j++) bs[SLOT * S + j] = z[j];
 }
