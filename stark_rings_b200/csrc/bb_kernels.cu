@@ -33,25 +33,8 @@ bb_ring_mul_half_kernel(const u64* a, const u64* b, u64* out, size_t n) {
         stage_in<R, T>(sB, b + e0 * R::WORDS64, ne);
         __syncthreads();
         u32 A[36], B[36], Y[36];
-#if defined(SR_BB_CRT_LOOP)
-        {   // ONE copy of the forward transform for both operands (opaque trip count): 11 KB less code
-            int trips = 2;
-            asm volatile("" : "+r"(trips));
-#pragma unroll
-            for (int i = 0; i < 36; i++) B[i] = 0;
-            const u32* src = sA + el * R::ROW;
-#pragma unroll 1
-            for (int k = 0; k < trips; k++) {
-#pragma unroll
-                for (int i = 0; i < 36; i++) A[i] = B[i];
-                bb::half_crt(B, src, K);
-                src += (sB - sA);
-            }
-        }
-#else
         bb::half_crt(A, sA + el * R::ROW, K);
         bb::half_crt(B, sB + el * R::ROW, K);
-#endif
         bb::half_slots(B, A, K);
         bb::half_icrt_local(B, K);
 #pragma unroll
@@ -87,7 +70,9 @@ static cudaError_t launch_ring_mul_half(const u64* a, const u64* b, u64* out, si
 
 // Tuning (B200, n = 2^22, see profiles/r01_tuning.md): CRT / ICRT one thread per element, 128-thread CTAs, 3 per SM;
 // NTT-form product 64-thread CTAs, 4 per SM (0.88 vs 0.80 of the roofline at 128); fused ring mul two threads per
-// element, 2 warps per CTA, 8 CTAs per SM (16 warps, 127 registers).
+// element, 2 warps per CTA, 8 CTAs per SM (16 warps, 126 registers).  Round 2, with the Shoup twiddle multiplications
+// (0.817): 96-register builds with 9 / 10 CTAs per SM 0.651, 4 warps x 5 CTAs 0.749, 4 x 4 0.811; ONE copy of the forward
+// transform run for both operands in a two-trip loop (11 KB less code, 28 bytes spilled) 0.797.
 cudaError_t bb_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms) {
     switch (op) {
     case OP_CRT: return launch_batch_op<BBPolicy, OP_CRT, 128, 3>(a, b, out, n, st, sms);
