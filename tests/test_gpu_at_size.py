@@ -66,7 +66,7 @@ def test_goldilocks_commit_baseline_config4(S, kappa):
 
 @pytest.mark.parametrize("name,m", [("babybear", 1 << 15), ("babybear", (1 << 17) + 5), ("stark_prime", 1 << 15),
                                     ("stark_prime", (1 << 17) + 5)])
-@pytest.mark.parametrize("kappa", [1, 4, 5])
+@pytest.mark.parametrize("kappa", [1, 2, 3, 4, 5, 7])  # one / two row groups per CTA, a group with a missing row, 4 + 1, 4 + 3
 def test_babybear_starknet_commit_grid_wrap(S, name, m, kappa):
     _check_matvec(S, name, kappa, m, 7000 + kappa + m)
 
