@@ -82,11 +82,12 @@ static cudaError_t launch_sp_quad(const u64* a, const u64* b, u64* out, size_t n
 }
 
 // Tuning (B200, n = 2^20, profiles/r01b_gl_ncu.md): 2 warps x 12 CTAs = 24 warps per SM (80 registers) is the fastest
-// configuration for all four ops.
+// configuration; with the unreduced arithmetic of round 2 the ICRT gains 2% from 14 CTAs (72 registers; n = 2^22:
+// 2.404 against 2.451 ms), the CRT loses 2% (2.144 against 2.100 ms), 16 CTAs (64 registers) are no better.
 cudaError_t sp_launch(int op, const u64* a, const u64* b, u64* out, size_t n, cudaStream_t st, int sms) {
     switch (op) {
     case OP_CRT: return launch_sp_quad<OP_CRT, 2, 12>(a, b, out, n, st, sms);
-    case OP_ICRT: return launch_sp_quad<OP_ICRT, 2, 12>(a, b, out, n, st, sms);
+    case OP_ICRT: return launch_sp_quad<OP_ICRT, 2, 14>(a, b, out, n, st, sms);
     case OP_NTT_MUL: return launch_sp_quad<OP_NTT_MUL, 2, 12>(a, b, out, n, st, sms);
     case OP_RING_MUL: return launch_sp_quad<OP_RING_MUL, 2, 12>(a, b, out, n, st, sms);
     }
