@@ -698,7 +698,9 @@ def main():
             del bufs
             torch.cuda.empty_cache()
             extra.append(rec)
-        extra.append(measure_commit(env, "gl", 4, 20, max(args.steps, 40), args.warmup, args.commit_path,
+        # (a commitment is 35-200 us: a few hundred of them, after a few dozen untimed ones, so that the start-up skew of
+        # the ranks is not what is measured)
+        extra.append(measure_commit(env, "gl", 4, 20, max(args.steps, 400), max(args.warmup, 40), args.commit_path,
                                     not args.no_graph))
     env.sampler.stop()
 
