@@ -391,25 +391,6 @@ SR_HD void acc_mul(Acc& A, u64 a, u64 b) {
     A.o1 = (u32)o; A.o2 = (u32)(o >> 32); A.o3 = (u32)(o < lh);
 #endif
 }
-// Signed fold used by acc_reduce_m128: X + Y T for two's-complement X, Y with |X|, |Y| < 2^35, as V = X + Y T + 16 p > 0
-// (a 128-bit integer whose small high word is folded with 2^64 = 2^32 - 1).
-SR_HD u64 fold_xy(u64 X, u64 Y) {  // X, Y two's-complement 64-bit, |X|, |Y| < 2^35
-    // V = X + (Y << 32) + 16 p > 0 (|V| < 2^67 + 2^35, 16 p = 2^68 - 2^36 + 16): low 64 bits and the small high word
-    const u64 ylo = Y << 32;                       // (Y mod 2^32) * 2^32
-    const u64 yhi = (u64)((long long)Y >> 32);     // floor(Y / 2^32), sign-extended
-    const u64 xhi = (u64)((long long)X >> 63);     // 0 or -1
-    const u64 lo = X + ylo;
-    u64 hi = xhi + yhi + (lo < ylo ? 1u : 0u);
-    const u64 bias_lo = 16ull - (1ull << 36);      // 16 p = 15 * 2^64 + (2^64 - 2^36 + 16)
-    const u64 lo2 = lo + bias_lo;
-    hi += 15u + (lo2 < bias_lo ? 1u : 0u);
-    // hi in [1, 24]: lo2 + hi * (2^32 - 1), one possible wrap
-#if defined(__CUDA_ARCH__)
-    return canon(add_eps_mul(lo2, (u32)hi));
-#else
-    return canon(reduce128(lo2, hi));
-#endif
-}
 // Canonical residue of the accumulated value; valid for sums of fewer than 2^31 products.
 // Merge the two halves into limbs l0..l4 (one carry chain), then with T = 2^32, T^2 = 2^64 = 2^32 - 1 and T^3 = -1 (mod p):
 //   l0 + l1 T + l2 T^2 + (l3 + l4 T) T^3  =  [(l0, l1) + l2 (2^32 - 1)]  -  (l3, l4)
@@ -440,14 +421,35 @@ SR_HD u64 acc_reduce(const Acc& A) {
 #endif
 }
 // canonical residue of (accumulated value) * 2^128, i.e. with the Montgomery factor 2^-64 = 2^128 of a product of two
-// raw limbs folded into the reduction.  With T = 2^32: T^2 = T - 1, T^3 = -1, so T^4 .. T^8 = -T, 1 - T, 1, T, T - 1 and
-//   (l0 + l1 T + l2 T^2 + l3 T^3 + l4 T^4) T^4 = (l2 + l3 T) - l1 (T - 1) - l0 T + l4 (T - 1):
-// three modular additions of canonical terms instead of a reduction followed by a shift-reduction and a negation.
+// raw limbs folded into the reduction.  Limbs l0..l4 as in acc_reduce; with T = 2^32, T^2 = 2^32 - 1 and T^3 = -1 the powers
+// T^4 .. T^8 are -T, -T^2, 1, T, T^2, so
+//   (l0 + l1 T + l2 T^2 + l3 T^3 + l4 T^4) T^4 = [(l2, l3) + l4 (2^32 - 1)] - [(0, l0) + l1 (2^32 - 1)]:
+// two multiply-add folds and one modular subtraction, 23 instructions (the round-1 form, two signed 64-bit sums X + Y T
+// folded with a bias of 16 p, took 26: ntt_mul 0.742 -> 0.760 of the HBM roofline).
 SR_HD u64 acc_reduce_m128(const Acc& A) {
-    // (X + Y T) T^4 = -T (X + Y T) = Y - (X + Y) T
-    const u64 X = (u64)A.e0 - A.e2 - A.o2 - A.e3 - A.o3;
-    const u64 Y = (u64)A.e1 + A.o1 + A.e2 + A.o2 - A.e4;
-    return fold_xy(Y, (u64)0 - (X + Y));
+    u32 l1, l2, l3, l4;
+#if defined(__CUDA_ARCH__)
+    asm("add.cc.u32   %0, %4, %7;\n\t"
+        "addc.cc.u32  %1, %5, %8;\n\t"
+        "addc.cc.u32  %2, %6, %9;\n\t"
+        "addc.u32     %3, %10, 0;\n\t"
+        : "=&r"(l1), "=&r"(l2), "=&r"(l3), "=r"(l4)
+        : "r"(A.e1), "r"(A.e2), "r"(A.e3), "r"(A.o1), "r"(A.o2), "r"(A.o3), "r"(A.e4));
+    const u64 U = add_eps_mul(mk64(l2, l3), l4);
+    const u64 W = canon(add_eps_mul(mk64(0u, A.e0), l1));
+    return canon(sub(U, W));
+#else
+    u64 t = (u64)A.e1 + A.o1;
+    l1 = (u32)t;
+    t = (u64)A.e2 + A.o2 + (t >> 32);
+    l2 = (u32)t;
+    t = (u64)A.e3 + A.o3 + (t >> 32);
+    l3 = (u32)t;
+    l4 = A.e4 + (u32)(t >> 32);
+    const u64 U = reduce128(mk64(l2, l3), (u64)l4);
+    const u64 W = reduce128(mk64(0u, A.e0), (u64)l1);
+    return canon(sub(U, W));
+#endif
 }
 // canonical a ka + b kb (+ c kc + d kd): weak inputs, one reduction
 SR_HD u64 dot2(u64 a, u64 ka, u64 b, u64 kb) {
