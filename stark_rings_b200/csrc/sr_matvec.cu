@@ -375,6 +375,9 @@ static cudaError_t gl_k6_launch(const u64* const* d_rows, size_t nrows, size_t r
 #ifndef SR_MV_RB
 #define SR_MV_RB 4
 #endif
+#ifndef SR_MV_BB_PREFETCH
+#define SR_MV_BB_PREFETCH 1  // BabyBear: next trip's loads before this trip's products
+#endif
 #ifndef SR_MV_BB_GROUPS
 #define SR_MV_BB_GROUPS 2  // BabyBear: row groups per CTA (matvec_partial_kernel)
 #endif
@@ -388,7 +391,7 @@ constexpr int MV_T = SR_MV_T;  // threads per CTA (multiple of every SLOTS)
 // G thread groups per CTA split the RB rows of the pass between them (BabyBear: two groups of two rows, 36 accumulator
 // registers per thread instead of 72, which keeps two CTAs per SM resident); the groups walk the same slots, so the
 // second group's reads of v hit L1.
-template <class S, int RB, int G>
+template <class S, int RB, int G, bool PF = false>
 __global__ void __launch_bounds__(MV_T)
 matvec_partial_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t row0, size_t ncols,
                       const u64* __restrict__ v, MvTail tail) {
@@ -406,15 +409,48 @@ matvec_partial_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t 
 
     const size_t total = ncols * S::SLOTS;  // slots per row
     const size_t stride = (size_t)gridDim.x * TG;
-    for (size_t g = (size_t)blockIdx.x * TG + tl; g < total; g += stride) {
-        const typename S::Prep x = S::prep(S::load_cached(v + g * S::SLOT_U64));
-        typename S::Val a[RPT];
+    if (PF) {
+        // software pipeline: the loads of the next trip are issued before this trip's products (ncu of the unreduced
+        // BabyBear kernel: long_scoreboard 4.0 warps per issue, the multiply-add pipe 62 % busy)
+        size_t g = (size_t)blockIdx.x * TG + tl;
+        typename S::Val xn = S::zero(), an[RPT];
 #pragma unroll
-        for (int r = 0; r < RPT; r++)
-            if (rp[r]) a[r] = S::load(rp[r] + g * S::SLOT_U64);
+        for (int r = 0; r < RPT; r++) an[r] = S::zero();
+        if (g < total) {
+            xn = S::load_cached(v + g * S::SLOT_U64);
 #pragma unroll
-        for (int r = 0; r < RPT; r++)
-            if (rp[r]) S::accum_mad_p(acc[r], a[r], x);
+            for (int r = 0; r < RPT; r++)
+                if (rp[r]) an[r] = S::load(rp[r] + g * S::SLOT_U64);
+        }
+        while (g < total) {
+            const typename S::Val xc = xn;
+            typename S::Val a[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; r++) a[r] = an[r];
+            const size_t g2 = g + stride;
+            if (g2 < total) {
+                xn = S::load_cached(v + g2 * S::SLOT_U64);
+#pragma unroll
+                for (int r = 0; r < RPT; r++)
+                    if (rp[r]) an[r] = S::load(rp[r] + g2 * S::SLOT_U64);
+            }
+            const typename S::Prep x = S::prep(xc);
+#pragma unroll
+            for (int r = 0; r < RPT; r++)
+                if (rp[r]) S::accum_mad_p(acc[r], a[r], x);
+            g = g2;
+        }
+    } else {
+        for (size_t g = (size_t)blockIdx.x * TG + tl; g < total; g += stride) {
+            const typename S::Prep x = S::prep(S::load_cached(v + g * S::SLOT_U64));
+            typename S::Val a[RPT];
+#pragma unroll
+            for (int r = 0; r < RPT; r++)
+                if (rp[r]) a[r] = S::load(rp[r] + g * S::SLOT_U64);
+#pragma unroll
+            for (int r = 0; r < RPT; r++)
+                if (rp[r]) S::accum_mad_p(acc[r], a[r], x);
+        }
     }
     pdl_wait();  // the previous kernel on the stream (its tail reads the scratch this one is about to write) is done
     pdl_launch_dependents();
@@ -562,6 +598,7 @@ static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nr
             else e = gl_k6_launch<SR_GLK_SHAPE_1>(d_rows, nrows, row0, ncols, v, tail, mg, st, sms, pdl);
         } else if constexpr (!std::is_same<S, GLSlot>::value) {
             constexpr int G = std::is_same<S, BBSlot>::value ? SR_MV_BB_GROUPS : 1;
+            constexpr bool PF = std::is_same<S, BBSlot>::value && SR_MV_BB_PREFETCH;  // (Starknet: 32 more registers than fit)
             const size_t total = ncols * S::SLOTS;
             int grid = mv_grid(sms);
             const size_t need = (total + MV_T / G - 1) / (MV_T / G);
@@ -571,11 +608,11 @@ static cudaError_t matvec_launch_t(int ring, const u64* const* d_rows, size_t nr
                 const size_t need1 = (total + MV_T - 1) / MV_T;
                 int grid1 = mv_grid(sms);
                 if ((size_t)grid1 > need1) grid1 = (int)need1;
-                e = launch_pdl(matvec_partial_kernel<S, RB / G, 1>, (unsigned)grid1, (unsigned)MV_T, 0, st, pdl, d_rows,
+                e = launch_pdl(matvec_partial_kernel<S, RB / G, 1, PF>, (unsigned)grid1, (unsigned)MV_T, 0, st, pdl, d_rows,
                                nrows, row0, ncols, v, tail);
             } else {
-                e = launch_pdl(matvec_partial_kernel<S, RB, G>, (unsigned)grid, (unsigned)MV_T, 0, st, pdl, d_rows, nrows,
-                               row0, ncols, v, tail);
+                e = launch_pdl(matvec_partial_kernel<S, RB, G, PF>, (unsigned)grid, (unsigned)MV_T, 0, st, pdl, d_rows,
+                               nrows, row0, ncols, v, tail);
             }
         }
         if (e != cudaSuccess) return e;
