@@ -114,13 +114,10 @@ SR_HD void sextic_products(u64* rowA, const u64* rowB) {
     }
 }
 
-#ifndef SR_GL_TAIL4
-#define SR_GL_TAIL4 0  // 1: weak rows take four products per output (no canonicalisation, twice the wide multiply-adds)
-#endif
 // The last two inverse stages (ntt.rs:272-318) in place on the row as constant-coefficient sums (gl_ring.cuh, TailK),
 // two coefficient quadruples (i, i + 6, i + 12, i + 18) per trip.  CANON_IN: the second and fourth quarter of the row
-// hold canonical values (sums and differences first, two products per output); otherwise weak values (the subtrahends are canonicalised first; measured
-// against four products per output with no canonicalisation, SR_GL_TAIL4).  Output canonical.
+// hold canonical values (sums and differences first, two products per output); otherwise weak values (the subtrahends are canonicalised first: four
+// products per output with no canonicalisation were measured slower, twice the wide multiply-adds).  Output canonical.
 template <class K, bool CANON_IN>
 SR_HD void tail_rows(u64* row) {
     SR_GL_ROLL
@@ -133,7 +130,6 @@ SR_HD void tail_rows(u64* row) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             if (CANON_IN) tail_dot2<K>(o0[u], o1[u], o2[u], o3[u], u0[u], u1[u], u2[u], u3[u]);
-            else if (SR_GL_TAIL4) tail_dot4<K>(o0[u], o1[u], o2[u], o3[u], u0[u], u1[u], u2[u], u3[u]);
             else tail_dot2<K>(o0[u], o1[u], o2[u], o3[u], u0[u], canon(u1[u]), u2[u], canon(u3[u]));
         }
         st2(row + 2 * t, o0[0], o0[1]);

@@ -451,19 +451,11 @@ SR_HD u64 acc_reduce_m128(const Acc& A) {
     return canon(sub(U, W));
 #endif
 }
-// canonical a ka + b kb (+ c kc + d kd): weak inputs, one reduction
+// canonical a ka + b kb: weak inputs, one reduction
 SR_HD u64 dot2(u64 a, u64 ka, u64 b, u64 kb) {
     Acc d;
     acc_mul(d, a, ka);
     acc_mad(d, b, kb);
-    return acc_reduce(d);
-}
-SR_HD u64 dot4(u64 a, u64 ka, u64 b, u64 kb, u64 c, u64 kc, u64 e, u64 ke) {
-    Acc d;
-    acc_mul(d, a, ka);
-    acc_mad(d, b, kb);
-    acc_mad(d, c, kc);
-    acc_mad(d, e, ke);
     return acc_reduce(d);
 }
 
@@ -488,14 +480,6 @@ struct TailK {
     static constexpr u64 C0 = cmulm(A0, W22), C1 = cmulm(A1, W14);
     static constexpr u64 D0 = cmulm(B0, W22), D1 = cmulm(B1, W14);
 };
-// weak u0..u3 -> the four canonical outputs; four products per output, no additions on 64-bit residues
-template <class K>
-SR_HD void tail_dot4(u64& o0, u64& o1, u64& o2, u64& o3, u64 u0, u64 u1, u64 u2, u64 u3) {
-    o0 = dot4(u0, K::A0, u1, K::A0, u2, K::A1, u3, K::A1);
-    o1 = dot4(u0, K::C0, u1, P - K::C0, u2, K::C1, u3, P - K::C1);
-    o2 = dot4(u0, K::B0, u1, K::B0, u2, K::B1, u3, K::B1);
-    o3 = dot4(u0, K::D0, u1, P - K::D0, u2, K::D1, u3, P - K::D1);
-}
 // u0, u2 weak, u1, u3 CANONICAL -> the four canonical outputs; sums and differences first, two products per output
 template <class K>
 SR_HD void tail_dot2(u64& o0, u64& o1, u64& o2, u64& o3, u64 u0, u64 u1, u64 u2, u64 u3) {
@@ -546,7 +530,8 @@ SR_HD void icrt(u64 (&c)[D]) {
     icrt_stage1(o);
     typedef TailK<189, 190> K;
 #pragma unroll
-    for (int i = 0; i < 6; i++) tail_dot4<K>(c[i], c[6 + i], c[12 + i], c[18 + i], o[i], o[6 + i], o[12 + i], o[18 + i]);
+    for (int i = 0; i < 6; i++)
+        tail_dot2<K>(c[i], c[6 + i], c[12 + i], c[18 + i], o[i], canon(o[6 + i]), o[12 + i], canon(o[18 + i]));
 }
 
 // z = x * y in F_p[u]/(u^3 - 2^RHO_EXP), then times 2^POST_EXP.  Weak in, weak out.
