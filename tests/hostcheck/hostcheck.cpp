@@ -98,6 +98,15 @@ void hc_sp_dot(const uint64_t* a, const uint64_t* x, size_t n, uint64_t* out) {
         memcpy(out + 4 * s, &r, 32);
     }
 }
+// the two reductions of a 160-bit carry-save accumulator given as raw limbs (e0..e4, o1..o3)
+void hc_gl_acc_reduce(const uint32_t* limbs, uint64_t* out) {
+    gl::Acc A;
+    A.e0 = limbs[0]; A.e1 = limbs[1]; A.e2 = limbs[2]; A.e3 = limbs[3]; A.e4 = limbs[4];
+    A.o1 = limbs[5]; A.o2 = limbs[6]; A.o3 = limbs[7];
+    out[0] = gl::acc_reduce(A);
+    out[1] = gl::acc_reduce_m128(A);
+    out[2] = gl::acc_reduce<false>(A);
+}
 void hc_gl_crt(uint64_t* e) { u64 c[24]; memcpy(c, e, 192); gl::crt(c); memcpy(e, c, 192); }
 void hc_gl_icrt(uint64_t* e) { u64 c[24]; memcpy(c, e, 192); gl::icrt(c); memcpy(e, c, 192); }
 void hc_gl_ntt_mul(uint64_t* a, const uint64_t* b) {

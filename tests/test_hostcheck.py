@@ -144,3 +144,27 @@ def test_sp_lazy_dot(hc):
         out = np.zeros(w, dtype=np.uint64)
         hc.hc_sp_dot(_p(aa), _p(xx), ctypes.c_size_t(m), _p(out))
         assert np.array_equal(out, want), m
+
+
+def test_gl_accumulator_reductions(hc):
+    """gl::acc_reduce / acc_reduce_m128 on ARBITRARY accumulator states (random and extreme limbs, not only the ones a
+    product sum reaches): value = sum e_k T^k + sum o_k T^k with T = 2^32, reduced mod p and times 2^128 mod p."""
+    p = O.MODELS["goldilocks"].p
+    rng = random.Random(77)
+    ext = [0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF]
+    cases = []
+    for _ in range(4000):
+        e = [rng.choice(ext) if rng.random() < 0.4 else rng.getrandbits(32) for _ in range(4)]
+        o = [rng.choice(ext) if rng.random() < 0.4 else rng.getrandbits(32) for _ in range(3)]
+        e4 = rng.choice([0, 1, 2, 5, 1 << 10, (1 << 20) - 1])  # carries out of 2^128: tiny by construction
+        cases.append(e + [e4] + o)
+    cases += [[0] * 8, [0xFFFFFFFF] * 4 + [0] + [0xFFFFFFFF] * 3, [1, 0, 0, 0, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0, 0, 1]]
+    out = np.zeros(3, dtype=np.uint64)
+    for c in cases:
+        e0, e1, e2, e3, e4, o1, o2, o3 = c
+        v = e0 + ((e1 + o1) << 32) + ((e2 + o2) << 64) + ((e3 + o3) << 96) + (e4 << 128)
+        limbs = np.array(c, dtype=np.uint32)
+        hc.hc_gl_acc_reduce(limbs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), _p(out))
+        assert int(out[0]) == v % p, c
+        assert int(out[1]) == (v << 128) % p, c
+        assert int(out[2]) % p == v % p, c
