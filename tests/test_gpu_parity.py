@@ -380,3 +380,54 @@ def test_concurrent_host_threads_one_context_each(S):
         t.join()
     shared.close()
     assert len(res2) == 4 and all(res2.values())
+
+
+def _boundary_raw(name, n, seed):
+    """Elements whose raw limbs are drawn from the values where the kernels' lazy arithmetic changes branch: 0, 1, p - 1,
+    p - 2, and the word / carry boundaries of each prime (2^32 - 1, 2^32, the high word all ones, 2^63, ...)."""
+    import random
+    M = O.MODELS[name]
+    p = M.p
+    if name == "goldilocks":
+        eps = (1 << 32) - 1
+        vals = [0, 1, 2, eps - 1, eps, eps + 1, 1 << 32, (1 << 63), (1 << 63) - 1, p - 1, p - 2, p - eps, p - eps - 1,
+                0xFFFFFFFF00000000, 0xFFFFFFFEFFFFFFFF, 0xFFFFFFFE00000001, 0x00000001FFFFFFFF, 0x8000000080000000]
+    elif name == "babybear":
+        vals = [0, 1, 2, p - 1, p - 2, 1 << 27, (1 << 27) - 1, 15 << 27, (1 << 30), (1 << 30) - 1, 0x77FFFFFF, 0x40000001]
+    else:
+        vals = [0, 1, 2, p - 1, p - 2, (1 << 251), (1 << 251) - 1, (1 << 192) * 17, (1 << 192) * 17 - 1, (1 << 224) - 1,
+                (1 << 128) - 1, (1 << 250) + (1 << 64) - 1, p - (1 << 192), p >> 1]
+    vals = [v % p for v in vals]
+    rng = random.Random(seed)
+    nl = 4 if name == "stark_prime" else 1  # u64 limbs per coefficient
+    out = []
+    for e in range(n):
+        for c in range(M.D):
+            v = vals[(e + c) % len(vals)] if e < len(vals) else rng.choice(vals)
+            for k in range(nl):
+                out.append((v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF)
+    return np.array(out, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_boundary_values_all_ops(S, name):
+    """crt / icrt / ntt_mul / ring_mul / mat-vec on raw limbs at the word and carry boundaries of each prime."""
+    cfg = S.CONFIGS[name]
+    n = 700
+    a, b = _boundary_raw(name, n, 1), _boundary_raw(name, n, 3)
+    b[: WORDS[name] * 64] = a[WORDS[name] * 3: WORDS[name] * 67]  # the deterministic patterns against each other, shifted
+    for op, want in (("crt", C.crt(name, a.copy(), threads=8)), ("icrt", C.icrt(name, a.copy(), threads=8))):
+        d = dev(a)
+        getattr(cfg, op + "_batch")(d)
+        assert np.array_equal(host(d), want), op
+    da, db = dev(a), dev(b)
+    cfg.ntt_mul_batch(da, db)
+    assert np.array_equal(host(da), C.ntt_mul(name, a.copy(), b.copy(), threads=8))
+    out = cfg.ring_mul_batch(dev(a), db)
+    assert np.array_equal(host(out), C.ring_mul(name, a, b, threads=8))
+    ctx = S.default_context(0)
+    rows = [_boundary_raw(name, n, 10 + i) for i in range(3)]
+    want = C.matvec(name, [r.copy() for r in rows], a.copy(), threads=3)
+    A = S.Matrix([S.RqNTT(cfg, dev(r), ctx) for r in rows], ctx)
+    got = A.try_mul_vec(S.RqNTT(cfg, dev(a), ctx))
+    assert np.array_equal(host(got.data), want)
