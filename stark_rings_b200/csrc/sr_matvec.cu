@@ -271,13 +271,6 @@ gl_matvec_k6_kernel(const u64* const* __restrict__ rows, size_t nrows, size_t ro
         }
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
-#if defined(SR_GLK_NOCOMPUTE)  // experiment: the data path alone (results are wrong)
-#pragma unroll
-        for (int q = 0; q < SPT; q++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) { P0.e0 ^= (u32)x[q][k] ^ (u32)(a[q][k] >> 32); P0.e1 += (u32)a[q][k]; }
-        return;
-#endif
 #pragma unroll
         for (int q = 0; q < SPT; q++) {
             // limbs in memory are canonical, so the weak-form additions are exact residues (a + b, b canonical)
